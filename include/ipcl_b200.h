@@ -1,0 +1,162 @@
+/*
+ * ipcl_b200.h -- C ABI of the B200 (sm_100a) back-end for the modexp hot path
+ * of intel/pailliercryptolib (IPCL v2.0.0).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch
+ * types.  It occupies the slot the reference's QAT offload occupies
+ * (ipcl/mod_exp.cpp:68-184 calling HE_QAT_bnModExp_MT,
+ * module/heqat/heqat/include/heqat/bnops.h:121-148): marshal a batch into flat
+ * buffers, submit, wait, unmarshal.  The C++ `ipcl::` layer in
+ * pailliercryptolib_b200/ipcl/ is the reference-side caller.
+ *
+ * Number format everywhere: little-endian arrays of 32-bit words -- the layout
+ * ippsRef_BN exposes and ippMBModExp copies from (ipcl/mod_exp.cpp:472-476,
+ * 503-506) -- with a fixed stride per element, element-major.
+ *
+ * Every function returns 0 on success or a negative IPCLB200_ERR_* code (the
+ * convention of HE_QAT_STATUS, module/heqat/heqat/include/heqat/common/
+ * types.h:35-43); ipclb200_last_error() gives the text for the calling thread.
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with IPCLB200_ERR_NO_DEVICE.
+ *
+ * Host-pointer entry points copy in, compute and copy out synchronously.
+ * *_dev entry points take device pointers on the current device plus a CUDA
+ * stream (passed as void*) and only enqueue work.
+ * All entry points are re-entrant; concurrent callers are serialised per
+ * device inside the library (the reference's encrypt/decrypt are called
+ * concurrently on one key, test/test_cryptography.cpp:45-57).
+ */
+#ifndef IPCL_B200_H_
+#define IPCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPCLB200_OK 0
+#define IPCLB200_ERR_BAD_ARG (-1)      /* null pointer, zero/oversize width ... */
+#define IPCLB200_ERR_EVEN_MODULUS (-2) /* Montgomery needs an odd modulus      */
+#define IPCLB200_ERR_CUDA (-3)         /* a CUDA runtime call failed           */
+#define IPCLB200_ERR_NO_DEVICE (-4)    /* no usable sm_100 device              */
+#define IPCLB200_ERR_UNSUPPORTED (-5)  /* width not supported by this entry    */
+
+/* operand broadcast flags: the operand is ONE value used by every element
+ * (what std::vector<BigNumber>(sz, x) expresses at ipcl/pub_key.cpp:53-54,
+ * 68-69 and ipcl/pri_key.cpp:119-120) */
+#define IPCLB200_SHARED_BASE 1u
+#define IPCLB200_SHARED_EXP 2u
+#define IPCLB200_SHARED_MOD 4u
+/* modmul: the second factor is one value (the size-1 broadcast of
+ * CipherText::operator+, ipcl/ciphertext.cpp:51-59) */
+#define IPCLB200_SHARED_B 8u
+
+#define IPCLB200_MAX_MOD_WORDS 256 /* 8192-bit modulus */
+
+/* ---- runtime ------------------------------------------------------------ */
+/* replaces ipcl::initializeContext / terminateContext for this back-end
+ * (ipcl/utils/context.cpp:40-86).  device < 0 selects the current device (or
+ * LOCAL_RANK when set).  Idempotent. */
+int ipclb200_init(int device);
+void ipclb200_shutdown(void);
+int ipclb200_device_count(void);
+const char* ipclb200_last_error(void);
+const char* ipclb200_version(void);
+
+/* ---- batched modular exponentiation --------------------------------------
+ * out[i] = base[i] ^ exp[i] mod mod[i], 0 <= out[i] < mod[i].
+ * Replaces ipcl::ippModExp(vector, vector, vector), ipcl/mod_exp.cpp:655-678
+ * (and through it ippMBModExp :446-533 -> mbx_exp_mb8, ippSBModExp :535-585).
+ *   base : count x mod_words   (1 x mod_words with IPCLB200_SHARED_BASE)
+ *   exp  : count x exp_words   (1 x exp_words with IPCLB200_SHARED_EXP)
+ *   mod  : count x mod_words   (1 x mod_words with IPCLB200_SHARED_MOD)
+ *   out  : count x mod_words
+ * base may be >= mod (it is reduced); mod must be odd and non-zero;
+ * exp == 0 gives 1 mod m. */
+int ipclb200_modexp(const uint32_t* base, const uint32_t* exp,
+                    const uint32_t* mod, int mod_words, int exp_words,
+                    size_t count, unsigned flags, uint32_t* out);
+
+/* Device-resident variant.  Requires IPCLB200_SHARED_MOD (mod is a HOST
+ * pointer: the per-modulus constants are derived on the host once) and
+ * mod_words in {16,32,48,64,96,128,192,256}.  exp_bits: number of significant
+ * exponent bits over the whole batch (0 = exp_words*32).  base/exp/out are
+ * device pointers, strides as above. */
+int ipclb200_modexp_dev(const uint32_t* d_base, const uint32_t* d_exp,
+                        const uint32_t* h_mod, int mod_words, int exp_words,
+                        int exp_bits, size_t count, unsigned flags,
+                        uint32_t* d_out, void* stream);
+
+/* ---- batched modular multiplication ---------------------------------------
+ * out[i] = a[i] * b[i] mod mod, one modulus for the batch.
+ * Replaces CipherText::raw_add (ct + ct), ipcl/ciphertext.cpp:135-141 and the
+ * loops :53-69; also BigNumber::ModMul at ipcl/pub_key.cpp:88-89. */
+int ipclb200_modmul(const uint32_t* a, const uint32_t* b, const uint32_t* mod,
+                    int mod_words, size_t count, unsigned flags, uint32_t* out);
+int ipclb200_modmul_dev(const uint32_t* d_a, const uint32_t* d_b,
+                        const uint32_t* h_mod, int mod_words, size_t count,
+                        unsigned flags, uint32_t* d_out, void* stream);
+
+/* ---- Paillier public key: encrypt ------------------------------------------
+ * Holds n, n^2 and (DJN) hs plus their device-side constants and the
+ * fixed-base table for hs.  Replaces the state of ipcl::PublicKey that the
+ * hot path reads (ipcl/pub_key.cpp:18-49). */
+typedef struct ipclb200_pubkey ipclb200_pubkey;
+
+/* n: n_words words (n_words*32 >= key bits).  hs: 2*n_words words or NULL for
+ * a non-DJN key.  rand_bits: DJN obfuscator exponent width (bits/2,
+ * ipcl/pub_key.cpp:46), ignored without hs. */
+int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs,
+                           int rand_bits, ipclb200_pubkey** out);
+void ipclb200_pubkey_destroy(ipclb200_pubkey* pk);
+
+/* ct[i] = ((n*pt[i] + 1) mod n^2) * obf[i] mod n^2,
+ *   obf[i] = hs^r[i] mod n^2 (DJN) or r[i]^n mod n^2 (non-DJN).
+ * Replaces PublicKey::raw_encrypt + applyObfuscator + get{DJN,Normal}
+ * Obfuscator, ipcl/pub_key.cpp:51-110.  The randoms r are supplied by the
+ * caller (host RNG stays in the ipcl:: layer, as setRandom injects them at
+ * ipcl/pub_key.cpp:92-95).  make_secure == 0 skips the obfuscator
+ * (ipcl/pub_key.cpp:107; r may be NULL).
+ *   pt: count x pt_words (pt_words <= n_words), r: count x r_words
+ *   (r_words <= 2*n_words), ct: count x 2*n_words. */
+int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt,
+                     int pt_words, const uint32_t* r, int r_words, size_t count,
+                     int make_secure, uint32_t* ct);
+int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt,
+                         int pt_words, const uint32_t* d_r, int r_words,
+                         size_t count, int make_secure, uint32_t* d_ct,
+                         void* stream);
+
+/* ---- Paillier private key: decrypt ------------------------------------------
+ * Derives p^2, q^2, p^-1 mod q, hp, hq (and lambda, x for the non-CRT path)
+ * exactly as the PrivateKey constructor does, ipcl/pri_key.cpp:13-37,159-167.
+ * p and q: p_words words each; they are ordered p < q internally (:19-22). */
+typedef struct ipclb200_privkey ipclb200_privkey;
+int ipclb200_privkey_create(const uint32_t* p, const uint32_t* q, int p_words,
+                            ipclb200_privkey** out);
+void ipclb200_privkey_destroy(ipclb200_privkey* sk);
+
+/* pt[i] = Dec(ct[i]).  use_crt != 0: PrivateKey::decryptCRT,
+ * ipcl/pri_key.cpp:114-152; use_crt == 0: decryptRAW, :92-111.
+ *   ct: count x 4*p_words (values < n^2), pt: count x 2*p_words. */
+int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct,
+                     size_t count, int use_crt, uint32_t* pt);
+int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
+                         size_t count, int use_crt, uint32_t* d_pt,
+                         void* stream);
+
+/* ---- measurement helpers --------------------------------------------------
+ * Runs the integer-pipe microbenchmark (dependent-carry IMAD.WIDE.U32 chains on
+ * every SM) and returns the measured 32x32->64 multiply-accumulate rate; this
+ * is the roofline denominator SURVEY.md section 8(d) asks the builder to
+ * measure.  Also returns the kernel-launch count since init (for bench.py's
+ * gpu_launches). */
+int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz);
+uint64_t ipclb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPCL_B200_H_ */

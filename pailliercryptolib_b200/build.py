@@ -1,0 +1,113 @@
+"""In-tree builds: the sm_100a CUDA library behind include/ipcl_b200.h, the
+C++ `ipcl::` host layer on top of it, and (test infrastructure) the C oracle.
+
+Everything is compiled with explicit nvcc / g++ / gcc command lines into
+directories next to the sources, so the artefacts travel with a snapshot of
+the repository (no JIT cache, no site-packages install)."""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pailliercryptolib_b200")
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+ORACLE = os.path.join(ROOT, "oracle")
+
+CUDA_LIB = os.path.join(LIBDIR, "libipcl_b200.so")
+IPCL_LIB = os.path.join(LIBDIR, "libipcl.so")
+ORACLE_LIB = os.path.join(ORACLE, "_build", "libpaillier_oracle.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+    "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_cuda(force=False, verbose=False):
+    """libipcl_b200.so: kernels + C ABI (nvcc, sm_100a only)."""
+    srcs = [os.path.join(CSRC, f) for f in
+            ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "hostbn.hpp")]
+    srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))
+    if not force and _newer(CUDA_LIB, srcs):
+        return CUDA_LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", CUDA_LIB, os.path.join(CSRC, "ipcl_b200.cu")]
+    out = _run(cmd)
+    if verbose:
+        print(out)
+    return CUDA_LIB
+
+
+def ipcl_sources():
+    d = os.path.join(PKG, "ipcl", "src")
+    if not os.path.isdir(d):
+        return []
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cpp"))
+
+
+def build_ipcl(force=False):
+    """libipcl.so: the C++ ipcl:: API mirror (g++), linked against the C ABI."""
+    srcs = ipcl_sources()
+    if not srcs:
+        return None
+    inc = os.path.join(PKG, "ipcl", "include")
+    hdrs = []
+    for base, _, files in os.walk(inc):
+        hdrs += [os.path.join(base, f) for f in files]
+    hdrs.append(os.path.join(CSRC, "hostbn.hpp"))
+    build_cuda()
+    if not force and _newer(IPCL_LIB, srcs + hdrs + [CUDA_LIB]):
+        return IPCL_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
+           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-o", IPCL_LIB] + srcs + [
+           "-L", LIBDIR, "-lipcl_b200", "-Wl,-rpath,$ORIGIN"]
+    _run(cmd)
+    return IPCL_LIB
+
+
+def build_oracle(force=False):
+    """oracle/_build/libpaillier_oracle.so -- the checker, never the product."""
+    src = os.path.join(ORACLE, "paillier_oracle.c")
+    extra = [os.path.join(ORACLE, f) for f in ("ifma_modexp.c",)
+             if os.path.exists(os.path.join(ORACLE, f))]
+    if not force and _newer(ORACLE_LIB, [src] + extra):
+        return ORACLE_LIB
+    os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
+    _run(["make", "-C", ORACLE, "-s"])
+    return ORACLE_LIB
+
+
+def build_all(force=False, verbose=False):
+    build_cuda(force, verbose)
+    build_ipcl(force)
+    build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", CUDA_LIB, IPCL_LIB if os.path.exists(IPCL_LIB) else "",
+          ORACLE_LIB)

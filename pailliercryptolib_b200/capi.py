@@ -1,0 +1,198 @@
+"""ctypes binding of the C ABI in include/ipcl_b200.h.
+
+This is the driver the parity tests and bench.py use to reach the library the
+same way a foreign-language host would: plain pointers and sizes.  Arrays are
+numpy uint32, little-endian limbs, shape (count, words).  There is no CPU
+fallback here or below: if the CUDA library is missing or no sm_100 device is
+present, calls raise."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+SHARED_BASE, SHARED_EXP, SHARED_MOD, SHARED_B = 1, 2, 4, 8
+
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_lib = None
+
+
+class IpclB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ipcl_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+EXPORTS = [
+    "ipclb200_init", "ipclb200_shutdown", "ipclb200_device_count",
+    "ipclb200_last_error", "ipclb200_version", "ipclb200_modexp",
+    "ipclb200_modexp_dev", "ipclb200_modmul", "ipclb200_modmul_dev",
+    "ipclb200_pubkey_create", "ipclb200_pubkey_destroy", "ipclb200_encrypt",
+    "ipclb200_encrypt_dev", "ipclb200_privkey_create",
+    "ipclb200_privkey_destroy", "ipclb200_decrypt", "ipclb200_decrypt_dev",
+    "ipclb200_int_peak", "ipclb200_launch_count",
+]
+
+
+def lib():
+    """Load libipcl_b200.so (must have been built in-tree; never built here
+    on the fly on a GPU box without nvcc)."""
+    global _lib
+    if _lib is None:
+        path = _build.CUDA_LIB
+        if not os.path.exists(path):
+            raise ImportError(
+                "%s is missing: run `python -m pailliercryptolib_b200.build` "
+                "(the CUDA extension is mandatory, there is no fallback)" % path)
+        L = ctypes.CDLL(path)
+        L.ipclb200_last_error.restype = ctypes.c_char_p
+        L.ipclb200_version.restype = ctypes.c_char_p
+        L.ipclb200_launch_count.restype = ctypes.c_uint64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise IpclB200Error(rc, lib().ipclb200_last_error().decode())
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_u32p)
+
+
+def _vp(x):
+    return ctypes.c_void_p(int(x))
+
+
+def init(device=-1):
+    _check(lib().ipclb200_init(int(device)))
+
+
+def shutdown():
+    lib().ipclb200_shutdown()
+
+
+def device_count():
+    return lib().ipclb200_device_count()
+
+
+def launch_count():
+    return int(lib().ipclb200_launch_count())
+
+
+def int_peak():
+    macs, mhz = ctypes.c_double(), ctypes.c_double()
+    _check(lib().ipclb200_int_peak(ctypes.byref(macs), ctypes.byref(mhz)))
+    return macs.value, mhz.value
+
+
+def modexp(base, exp, mod, flags=0):
+    base, exp, mod = _c(base), _c(exp), _c(mod)
+    base2, exp2, mod2 = np.atleast_2d(base), np.atleast_2d(exp), np.atleast_2d(mod)
+    count = max(base2.shape[0], exp2.shape[0], mod2.shape[0])
+    mw, ew = mod2.shape[1], exp2.shape[1]
+    assert base2.shape[1] == mw
+    out = np.zeros((count, mw), dtype=np.uint32)
+    _check(lib().ipclb200_modexp(_p(base2), _p(exp2), _p(mod2), mw, ew,
+                                 ctypes.c_size_t(count), flags, _p(out)))
+    return out
+
+
+def modmul(a, b, mod, flags=0):
+    a, b, mod = np.atleast_2d(_c(a)), np.atleast_2d(_c(b)), _c(mod)
+    mw = mod.shape[-1]
+    out = np.zeros_like(a)
+    _check(lib().ipclb200_modmul(_p(a), _p(b), _p(mod), mw,
+                                 ctypes.c_size_t(a.shape[0]), flags, _p(out)))
+    return out
+
+
+class PubKey:
+    def __init__(self, n, hs=None, rand_bits=0):
+        n = _c(n)
+        self.n_words = n.shape[-1]
+        self._h = ctypes.c_void_p()
+        hs_a = None if hs is None else _c(hs)
+        _check(lib().ipclb200_pubkey_create(_p(n), self.n_words, _p(hs_a),
+                                            int(rand_bits), ctypes.byref(self._h)))
+
+    def encrypt(self, pt, r=None, make_secure=True):
+        pt = np.atleast_2d(_c(pt))
+        r_a = None if r is None else np.atleast_2d(_c(r))
+        ct = np.zeros((pt.shape[0], 2 * self.n_words), dtype=np.uint32)
+        _check(lib().ipclb200_encrypt(self._h, _p(pt), pt.shape[1], _p(r_a),
+                                      0 if r_a is None else r_a.shape[1],
+                                      ctypes.c_size_t(pt.shape[0]),
+                                      int(make_secure), _p(ct)))
+        return ct
+
+    def encrypt_dev(self, d_pt, pt_words, d_r, r_words, count, d_ct, stream,
+                    make_secure=True):
+        _check(lib().ipclb200_encrypt_dev(self._h, _vp(d_pt), pt_words, _vp(d_r),
+                                          r_words, ctypes.c_size_t(count),
+                                          int(make_secure), _vp(d_ct), _vp(stream)))
+
+    def close(self):
+        if self._h:
+            lib().ipclb200_pubkey_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PrivKey:
+    def __init__(self, p, q):
+        p, q = _c(p), _c(q)
+        self.p_words = p.shape[-1]
+        self._h = ctypes.c_void_p()
+        _check(lib().ipclb200_privkey_create(_p(p), _p(q), self.p_words,
+                                             ctypes.byref(self._h)))
+
+    def decrypt(self, ct, use_crt=True):
+        ct = np.atleast_2d(_c(ct))
+        assert ct.shape[1] == 4 * self.p_words
+        pt = np.zeros((ct.shape[0], 2 * self.p_words), dtype=np.uint32)
+        _check(lib().ipclb200_decrypt(self._h, _p(ct), ctypes.c_size_t(ct.shape[0]),
+                                      int(use_crt), _p(pt)))
+        return pt
+
+    def decrypt_dev(self, d_ct, count, d_pt, stream, use_crt=True):
+        _check(lib().ipclb200_decrypt_dev(self._h, _vp(d_ct), ctypes.c_size_t(count),
+                                          int(use_crt), _vp(d_pt), _vp(stream)))
+
+    def close(self):
+        if self._h:
+            lib().ipclb200_privkey_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def modexp_dev(d_base, d_exp, mod, exp_words, exp_bits, count, d_out, stream,
+               flags=SHARED_MOD):
+    mod = _c(mod)
+    _check(lib().ipclb200_modexp_dev(_vp(d_base), _vp(d_exp), _p(mod),
+                                     mod.shape[-1], exp_words, exp_bits,
+                                     ctypes.c_size_t(count), flags, _vp(d_out),
+                                     _vp(stream)))
+
+
+def modmul_dev(d_a, d_b, mod, count, d_out, stream, flags=0):
+    mod = _c(mod)
+    _check(lib().ipclb200_modmul_dev(_vp(d_a), _vp(d_b), _p(mod), mod.shape[-1],
+                                     ctypes.c_size_t(count), flags, _vp(d_out),
+                                     _vp(stream)))

@@ -1,0 +1,1110 @@
+// ipcl_b200.cu -- implementation of the C ABI in include/ipcl_b200.h.
+//
+// Host side of the boundary: argument checking, derivation of the per-modulus
+// Montgomery constants (hostbn.hpp), staging of the flat limb buffers, launch
+// configuration, and the error convention.  All arithmetic on batch elements
+// happens in the kernels of kernels.cuh; nothing here falls back to the CPU.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ipcl_b200.h"
+#include "hostbn.hpp"
+#include "kernels.cuh"
+
+using namespace ipclb200;
+using hbn::Limbs;
+
+namespace {
+
+thread_local std::string t_err;
+
+int fail(int code, const std::string& msg) {
+  t_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                   \
+  do {                                                                   \
+    cudaError_t e_ = (expr);                                             \
+    if (e_ != cudaSuccess)                                               \
+      return fail(IPCLB200_ERR_CUDA,                                     \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// size classes: modulus words -> (limbs per lane K, lanes per integer T)
+// ---------------------------------------------------------------------------
+const int kClasses[] = {16, 32, 48, 64, 96, 128, 192, 256};
+
+int class_words(int words) {
+  for (int c : kClasses)
+    if (words <= c) return c;
+  return 0;
+}
+
+#define IPCLB200_DISPATCH(L, F)            \
+  switch (L) {                             \
+    case 16:  F(8, 2); break;              \
+    case 32:  F(16, 2); break;             \
+    case 48:  F(12, 4); break;             \
+    case 64:  F(16, 4); break;             \
+    case 96:  F(12, 8); break;             \
+    case 128: F(16, 8); break;             \
+    case 192: F(12, 16); break;            \
+    case 256: F(16, 16); break;            \
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
+  }
+
+int lanes_for(int L) {
+  switch (L) {
+    case 16: case 32: return 2;
+    case 48: case 64: return 4;
+    case 96: case 128: return 8;
+    default: return 16;
+  }
+}
+
+// fixed-window width minimising (2^w - 2) + bits + bits/w multiplies
+int pick_window(int ebits) {
+  int best = 1;
+  long best_cost = -1;
+  for (int w = 1; w <= kMaxWindow; w++) {
+    long cost = ((1L << w) - 2) + ebits + (ebits + w - 1) / w;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = w;
+    }
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------------------
+// per-modulus constants
+// ---------------------------------------------------------------------------
+struct DevModulus {
+  int L = 0;
+  Limbs n;
+  uint32_t* d = nullptr;  // [n | rr | r3 | one] each L words, then n0inv
+  const uint32_t* d_n0inv = nullptr;
+  ModConst mc{};
+  ~DevModulus() {
+    if (d) cudaFree(d);
+  }
+};
+
+struct HostModConst {
+  std::vector<uint32_t> n, rr, r3, one;
+  uint32_t n0inv;
+  uint32_t small_mod;
+};
+
+void host_mod_const(const Limbs& n, int L, HostModConst* h) {
+  Limbs R = hbn::pow2(32u * (unsigned)L);
+  Limbs one = hbn::mod(R, n);
+  Limbs rr = hbn::mod(hbn::mul(one, one), n);
+  Limbs r3 = hbn::mod(hbn::mul(rr, one), n);
+  h->n.resize(L);
+  h->rr.resize(L);
+  h->r3.resize(L);
+  h->one.resize(L);
+  hbn::to_words(n, h->n.data(), L);
+  hbn::to_words(rr, h->rr.data(), L);
+  hbn::to_words(r3, h->r3.data(), L);
+  hbn::to_words(one, h->one.data(), L);
+  h->n0inv = hbn::neg_inv32(n[0]);
+  h->small_mod = hbn::bitlen(n) <= 32 * L - 2 ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct Ctx {
+  std::mutex mu;
+  bool ready = false;
+  int device = -1;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  // grow-only scratch buffers for the host-pointer entry points
+  static const int kSlots = 8;
+  uint32_t* scratch[kSlots] = {};
+  size_t scratch_words[kSlots] = {};
+  // window-table workspace per stream
+  std::map<void*, std::pair<uint32_t*, size_t>> table_ws;
+  // small cache of shared moduli
+  std::vector<std::shared_ptr<DevModulus>> mod_cache;
+  std::atomic<uint64_t> launches{0};
+};
+
+Ctx g_ctx;
+
+int ensure_init_locked() {
+  if (g_ctx.ready) {
+    CUDA_TRY(cudaSetDevice(g_ctx.device));
+    return 0;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(IPCLB200_ERR_NO_DEVICE,
+                std::string("no CUDA device: ") + cudaGetErrorString(e));
+  int dev = 0;
+  if (const char* lr = getenv("LOCAL_RANK")) dev = atoi(lr) % ndev;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(IPCLB200_ERR_NO_DEVICE,
+                std::string("device is sm_") + std::to_string(prop.major) +
+                    std::to_string(prop.minor) +
+                    ", this library holds sm_100a code only");
+  CUDA_TRY(cudaSetDevice(dev));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  g_ctx.device = dev;
+  g_ctx.sms = prop.multiProcessorCount;
+  g_ctx.ready = true;
+  return 0;
+}
+
+int scratch_get(int slot, size_t words, uint32_t** out) {
+  if (g_ctx.scratch_words[slot] < words) {
+    if (g_ctx.scratch[slot]) {
+      CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+      CUDA_TRY(cudaFree(g_ctx.scratch[slot]));
+      g_ctx.scratch[slot] = nullptr;
+      g_ctx.scratch_words[slot] = 0;
+    }
+    size_t want = words + words / 4 + 1024;
+    CUDA_TRY(cudaMalloc(&g_ctx.scratch[slot], want * sizeof(uint32_t)));
+    g_ctx.scratch_words[slot] = want;
+  }
+  *out = g_ctx.scratch[slot];
+  return 0;
+}
+
+int table_ws_get(void* stream, size_t words, uint32_t** out) {
+  auto& slot = g_ctx.table_ws[stream];
+  if (slot.second < words) {
+    if (slot.first) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      CUDA_TRY(cudaFree(slot.first));
+      slot = {nullptr, 0};
+    }
+    uint32_t* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, words * sizeof(uint32_t)));
+    slot = {p, words};
+  }
+  *out = slot.first;
+  return 0;
+}
+
+int make_modulus(const Limbs& n, int L, std::shared_ptr<DevModulus>* out) {
+  for (auto& m : g_ctx.mod_cache)
+    if (m->L == L && m->n == n) {
+      *out = m;
+      return 0;
+    }
+  auto m = std::make_shared<DevModulus>();
+  HostModConst h;
+  host_mod_const(n, L, &h);
+  m->L = L;
+  m->n = n;
+  CUDA_TRY(cudaMalloc(&m->d, sizeof(uint32_t) * (4 * (size_t)L + 4)));
+  std::vector<uint32_t> blk;
+  blk.insert(blk.end(), h.n.begin(), h.n.end());
+  blk.insert(blk.end(), h.rr.begin(), h.rr.end());
+  blk.insert(blk.end(), h.r3.begin(), h.r3.end());
+  blk.insert(blk.end(), h.one.begin(), h.one.end());
+  blk.push_back(h.n0inv);
+  CUDA_TRY(cudaMemcpy(m->d, blk.data(), blk.size() * sizeof(uint32_t),
+                      cudaMemcpyHostToDevice));
+  m->mc.n = m->d;
+  m->mc.rr = m->d + L;
+  m->mc.r3 = m->d + 2 * L;
+  m->mc.one = m->d + 3 * L;
+  m->d_n0inv = m->d + 4 * L;
+  m->mc.n0inv = h.n0inv;
+  m->mc.small_mod = h.small_mod;
+  if (g_ctx.mod_cache.size() >= 16) g_ctx.mod_cache.erase(g_ctx.mod_cache.begin());
+  g_ctx.mod_cache.push_back(m);
+  *out = m;
+  return 0;
+}
+
+int check_modulus(const uint32_t* mod, int words, Limbs* out) {
+  Limbs n = hbn::from_words(mod, words);
+  if (n.empty()) return fail(IPCLB200_ERR_BAD_ARG, "modulus is zero");
+  if (!(n[0] & 1u))
+    return fail(IPCLB200_ERR_EVEN_MODULUS,
+                "modulus is even (Montgomery arithmetic needs an odd modulus)");
+  *out = n;
+  return 0;
+}
+
+// grid for a persistent kernel: enough blocks for `groups` groups, capped at
+// what is co-resident (a multiple of the SM count)
+template <typename Kern>
+int grid_for(Kern kern, size_t groups, int T, int* grid) {
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
+                                                         kBlockThreads, 0));
+  if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "kernel does not fit an SM");
+  size_t gpb = kBlockThreads / T;
+  size_t need = (groups + gpb - 1) / gpb;
+  size_t cap = (size_t)per_sm * g_ctx.sms;
+  *grid = (int)(need < cap ? need : cap);
+  if (*grid < 1) *grid = 1;
+  return 0;
+}
+
+int max_bits(const uint32_t* v, int words, size_t count, size_t stride) {
+  int best = 0;
+  for (size_t i = 0; i < count; i++) {
+    const uint32_t* e = v + i * stride;
+    for (int w = words - 1; w >= 0; w--) {
+      if (e[w]) {
+        int b = w * 32 + 32 - __builtin_clz(e[w]);
+        if (b > best) best = b;
+        break;
+      }
+      if ((w + 1) * 32 <= best) break;
+    }
+  }
+  return best;
+}
+
+// host (count x words) -> device (count x L), zero padded
+int upload_padded(uint32_t* d, const uint32_t* h, int words, int L,
+                  size_t count, cudaStream_t s) {
+  if (words == L) {
+    CUDA_TRY(cudaMemcpyAsync(d, h, count * (size_t)L * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(d, 0, count * (size_t)L * 4, s));
+    CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)L * 4, h, (size_t)words * 4,
+                               (size_t)words * 4, count, cudaMemcpyHostToDevice, s));
+  }
+  return 0;
+}
+int download_padded(uint32_t* h, const uint32_t* d, int words, int L,
+                    size_t count, cudaStream_t s) {
+  if (words == L) {
+    CUDA_TRY(cudaMemcpyAsync(h, d, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    CUDA_TRY(cudaMemcpy2DAsync(h, (size_t)words * 4, d, (size_t)L * 4,
+                               (size_t)words * 4, count, cudaMemcpyDeviceToHost, s));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers (device pointers, any stream)
+// ---------------------------------------------------------------------------
+int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
+  p.window = pick_window(p.exp_bits);
+  const int T = lanes_for(L);
+  int grid = 0;
+#define F(K_, T_)                                                         \
+  {                                                                       \
+    TRY(grid_for(modexp_kernel<K_, T_>, p.count, T_, &grid));             \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                  \
+    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),          \
+                     &p.table_ws));                                       \
+    modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
+  }
+  IPCLB200_DISPATCH(L, F)
+#undef F
+  (void)T;
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_modmul(ModmulParams p, int L, cudaStream_t s) {
+  int grid = 0;
+#define F(K_, T_)                                               \
+  {                                                             \
+    TRY(grid_for(modmul_kernel<K_, T_>, p.count, T_, &grid));   \
+    modmul_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);    \
+  }
+  IPCLB200_DISPATCH(L, F)
+#undef F
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// key objects
+// ---------------------------------------------------------------------------
+struct ipclb200_pubkey {
+  int nl = 0;  // words of n
+  int L = 0;   // class words of n^2
+  Limbs n, nsq, hs;
+  bool djn = false;
+  int rand_bits = 0;
+  std::shared_ptr<DevModulus> msq;
+  uint32_t* d_const = nullptr;  // [nR (L) | hs_m (L) | n as exponent (nl)]
+  // lazily built fixed-base comb table for hs
+  mutable uint32_t* d_comb = nullptr;
+  mutable int comb_w = 0;
+  mutable int comb_windows = 0;
+  ~ipclb200_pubkey() {
+    if (d_const) cudaFree(d_const);
+    if (d_comb) cudaFree(d_comb);
+  }
+};
+
+struct ipclb200_privkey {
+  int pl = 0;  // words of p (and q)
+  int L = 0;   // class words of p^2 (== 2*pl required)
+  Limbs p, q, n, nsq, lambda;
+  std::shared_ptr<DevModulus> mp2, mq2, mnsq;
+  uint32_t* d_const = nullptr;
+  // offsets into d_const (words)
+  const uint32_t *d_p = nullptr, *d_q = nullptr, *d_pm1 = nullptr,
+                 *d_qm1 = nullptr, *d_hpR = nullptr, *d_hqR = nullptr,
+                 *d_pinvR = nullptr, *d_n = nullptr, *d_muR = nullptr,
+                 *d_lambda = nullptr;
+  uint32_t p_inv32 = 0, q_inv32 = 0, p_n0inv = 0, q_n0inv = 0, n_inv32 = 0,
+           n_n0inv = 0;
+  int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
+  ~ipclb200_privkey() {
+    if (d_const) cudaFree(d_const);
+  }
+};
+
+namespace {
+
+// single modexp on the device through the batch kernel (key-setup scalars:
+// what the reference routes to ippSBModExp, ipcl/mod_exp.cpp:535-585)
+int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
+                  Limbs* out);
+
+int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
+                     const uint32_t* mod, int mod_words, int exp_words,
+                     size_t count, unsigned flags, uint32_t* out) {
+  const int L = class_words(mod_words);
+  if (!L) return fail(IPCLB200_ERR_UNSUPPORTED, "modulus wider than 8192 bits");
+  cudaStream_t s = g_ctx.stream;
+  const bool sh_mod = flags & IPCLB200_SHARED_MOD;
+  const bool sh_base = flags & IPCLB200_SHARED_BASE;
+  const bool sh_exp = flags & IPCLB200_SHARED_EXP;
+  ModexpParams p{};
+  p.count = count;
+  p.exp_words = exp_words;
+  p.exp_bits = max_bits(exp, exp_words, sh_exp ? 1 : count, exp_words);
+  std::shared_ptr<DevModulus> dm;
+  uint32_t* d_n0 = nullptr;
+  if (sh_mod) {
+    Limbs n;
+    TRY(check_modulus(mod, mod_words, &n));
+    TRY(make_modulus(n, L, &dm));
+    p.n = dm->mc.n;
+    p.rr = dm->mc.rr;
+    p.one = dm->mc.one;
+    p.mod_stride = 0;
+    p.n0_stride = 0;
+    p.n0inv = dm->d_n0inv;
+  } else {
+    // heterogeneous moduli (allowed by ippMBModExp, mod_exp.cpp:479-484; no
+    // in-tree caller uses it): per-element constants derived on the host
+    std::vector<uint32_t> hn(count * (size_t)L), hrr(count * (size_t)L),
+        hone(count * (size_t)L), hn0(count);
+    HostModConst h;
+    Limbs prev;
+    for (size_t i = 0; i < count; i++) {
+      Limbs n;
+      TRY(check_modulus(mod + i * (size_t)mod_words, mod_words, &n));
+      if (i == 0 || n != prev) host_mod_const(n, L, &h);
+      prev = n;
+      memcpy(&hn[i * (size_t)L], h.n.data(), (size_t)L * 4);
+      memcpy(&hrr[i * (size_t)L], h.rr.data(), (size_t)L * 4);
+      memcpy(&hone[i * (size_t)L], h.one.data(), (size_t)L * 4);
+      hn0[i] = h.n0inv;
+    }
+    uint32_t *dn, *drr, *done;
+    TRY(scratch_get(3, count * (size_t)L, &dn));
+    TRY(scratch_get(4, count * (size_t)L, &drr));
+    TRY(scratch_get(6, count * (size_t)L, &done));
+    TRY(scratch_get(5, count, &d_n0));
+    CUDA_TRY(cudaMemcpyAsync(dn, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(drr, hrr.data(), hrr.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(done, hone.data(), hone.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_n0, hn0.data(), hn0.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // host vectors die at scope end
+    p.n = dn;
+    p.rr = drr;
+    p.one = done;
+    p.n0inv = d_n0;
+    p.mod_stride = L;
+    p.n0_stride = 1;
+  }
+  uint32_t *d_base, *d_exp, *d_out;
+  TRY(scratch_get(0, (sh_base ? 1 : count) * (size_t)L, &d_base));
+  TRY(scratch_get(1, (sh_exp ? 1 : count) * (size_t)exp_words, &d_exp));
+  TRY(scratch_get(2, count * (size_t)L, &d_out));
+  TRY(upload_padded(d_base, base, mod_words, L, sh_base ? 1 : count, s));
+  CUDA_TRY(cudaMemcpyAsync(d_exp, exp, (sh_exp ? 1 : count) * (size_t)exp_words * 4,
+                           cudaMemcpyHostToDevice, s));
+  p.base = d_base;
+  p.base_stride = sh_base ? 0 : L;
+  p.exp = d_exp;
+  p.exp_stride = sh_exp ? 0 : exp_words;
+  p.out = d_out;
+  TRY(launch_modexp(p, L, s));
+  TRY(download_padded(out, d_out, mod_words, L, count, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
+                  Limbs* out) {
+  int mw = (int)mod.size();
+  int ew = e.empty() ? 1 : (int)e.size();
+  std::vector<uint32_t> b(mw), x(ew), m(mw), r(mw);
+  Limbs br = hbn::mod(base, mod);
+  hbn::to_words(br, b.data(), mw);
+  hbn::to_words(e, x.data(), ew);
+  hbn::to_words(mod, m.data(), mw);
+  TRY(modexp_host_impl(b.data(), x.data(), m.data(), mw, ew, 1,
+                       IPCLB200_SHARED_MOD, r.data()));
+  *out = hbn::from_words(r.data(), mw);
+  return 0;
+}
+
+int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
+  const int L = pk->L;
+  const int w = 8;
+  int windows = (bits + w - 1) / w;
+  if (windows < 1) windows = 1;
+  if (pk->d_comb && pk->comb_windows >= windows) return 0;
+  if (pk->d_comb) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(pk->d_comb));
+    pk->d_comb = nullptr;
+  }
+  size_t words = (size_t)windows * ((size_t)L << w);
+  CUDA_TRY(cudaMalloc(&pk->d_comb, words * sizeof(uint32_t)));
+  CombParams cp{};
+  cp.m = pk->msq->mc;
+  cp.hs_m = pk->d_const + L;
+  cp.comb = pk->d_comb;
+  cp.w = w;
+  cp.windows = windows;
+#define F(K_, T_)                                                       \
+  {                                                                     \
+    comb_spine_kernel<K_, T_><<<1, 32, 0, s>>>(cp);                     \
+    int gpb = kBlockThreads / T_;                                       \
+    int grid = (windows + gpb - 1) / gpb;                               \
+    comb_fill_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(cp);        \
+  }
+  IPCLB200_DISPATCH(L, F)
+#undef F
+  g_ctx.launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s));  // one-off; later users may be on other streams
+  pk->comb_w = w;
+  pk->comb_windows = windows;
+  return 0;
+}
+
+int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
+                     int pt_words, const uint32_t* d_r, int r_words,
+                     int r_bits, size_t count, int make_secure, uint32_t* d_ct,
+                     cudaStream_t s) {
+  const int L = pk->L;
+  EncryptParams p{};
+  p.pt = d_pt;
+  p.pt_words = pt_words;
+  p.r = d_r;
+  p.r_words = r_words;
+  p.r_bits = r_bits;
+  p.m = pk->msq->mc;
+  p.nR = pk->d_const;
+  p.hs_m = pk->d_const + L;
+  p.n_exp = pk->d_const + 2 * L;
+  p.n_exp_words = pk->nl;
+  p.ct = d_ct;
+  p.count = count;
+  p.window = 1;
+  if (!make_secure) {
+    p.mode = 0;
+  } else if (pk->djn) {
+    // comb needs count large enough to amortise the table build
+    const char* no_comb = getenv("IPCLB200_NO_COMB");
+    if (count >= 64 && !(no_comb && no_comb[0] == '1')) {
+      TRY(build_comb(pk, r_bits > pk->rand_bits ? r_bits : pk->rand_bits, s));
+      p.mode = 1;
+      p.comb = pk->d_comb;
+      p.comb_w = pk->comb_w;
+      p.comb_windows = (r_bits + pk->comb_w - 1) / pk->comb_w;
+      if (p.comb_windows < 1) p.comb_windows = 1;
+    } else {
+      p.mode = 2;
+      p.window = pick_window(r_bits);
+    }
+  } else {
+    p.mode = 3;
+    p.window = pick_window(pk->nl * 32);
+  }
+  int grid = 0;
+#define F(K_, T_)                                                          \
+  {                                                                        \
+    TRY(grid_for(encrypt_kernel<K_, T_>, count, T_, &grid));               \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
+    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),           \
+                     &p.table_ws));                                        \
+    encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
+  }
+  IPCLB200_DISPATCH(L, F)
+#undef F
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
+                     size_t count, int use_crt, uint32_t* d_pt,
+                     uint32_t* d_x /* count x 4*pl words scratch */,
+                     cudaStream_t s) {
+  const int pl = sk->pl;
+  if (use_crt) {
+    const int L = sk->L;
+    DecryptCrtParams p{};
+    p.ct = d_ct;
+    p.m[0] = sk->mp2->mc;
+    p.m[1] = sk->mq2->mc;
+    p.e[0] = sk->d_pm1;
+    p.e[1] = sk->d_qm1;
+    p.e_words = pl;
+    p.e_bits[0] = sk->pm1_bits;
+    p.e_bits[1] = sk->qm1_bits;
+    p.x = d_x;
+    p.count = count;
+    p.window = pick_window(sk->qm1_bits);
+    int grid = 0;
+#define F(K_, T_)                                                          \
+  {                                                                        \
+    TRY(grid_for(decrypt_crt_kernel<K_, T_>, 2 * count, T_, &grid));       \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
+    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),           \
+                     &p.table_ws));                                        \
+    decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
+  }
+    IPCLB200_DISPATCH(L, F)
+#undef F
+    CrtFinishParams f{};
+    f.x = d_x;
+    f.p = sk->d_p;
+    f.q = sk->d_q;
+    f.hpR = sk->d_hpR;
+    f.hqR = sk->d_hqR;
+    f.pinvR = sk->d_pinvR;
+    f.p_inv32 = sk->p_inv32;
+    f.q_inv32 = sk->q_inv32;
+    f.p_n0inv = sk->p_n0inv;
+    f.q_n0inv = sk->q_n0inv;
+    f.pl = pl;
+    f.xl = L;
+    f.pt = d_pt;
+    f.count = count;
+    crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
+    g_ctx.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    const int L = sk->mnsq->L;
+    ModexpParams p{};
+    p.base = d_ct;
+    p.base_stride = L;
+    p.exp = sk->d_lambda;
+    p.exp_stride = 0;
+    p.exp_words = 2 * pl;
+    p.exp_bits = sk->lambda_bits;
+    p.n = sk->mnsq->mc.n;
+    p.rr = sk->mnsq->mc.rr;
+    p.one = sk->mnsq->mc.one;
+    p.n0inv = sk->mnsq->d_n0inv;
+    p.mod_stride = 0;
+    p.n0_stride = 0;
+    p.out = d_x;
+    p.count = count;
+    TRY(launch_modexp(p, L, s));
+    RawFinishParams f{};
+    f.x = d_x;
+    f.n = sk->d_n;
+    f.muR = sk->d_muR;
+    f.n_inv32 = sk->n_inv32;
+    f.n_n0inv = sk->n_n0inv;
+    f.nl = 2 * pl;
+    f.xl = L;
+    f.pt = d_pt;
+    f.count = count;
+    raw_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
+    g_ctx.launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// exported C ABI
+// ===========================================================================
+extern "C" {
+
+const char* ipclb200_version(void) { return "ipcl_b200 0.1 (sm_100a)"; }
+const char* ipclb200_last_error(void) { return t_err.c_str(); }
+
+int ipclb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ipclb200_init(int device) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.ready && (device < 0 || device == g_ctx.device)) return 0;
+  if (g_ctx.ready)
+    return fail(IPCLB200_ERR_BAD_ARG, "already initialised on another device");
+  if (device >= 0) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev)
+      return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
+    char buf[16];
+    snprintf(buf, sizeof buf, "%d", device);
+    setenv("LOCAL_RANK", buf, 1);
+  }
+  return ensure_init_locked();
+}
+
+void ipclb200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (!g_ctx.ready) return;
+  cudaSetDevice(g_ctx.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < Ctx::kSlots; i++) {
+    if (g_ctx.scratch[i]) cudaFree(g_ctx.scratch[i]);
+    g_ctx.scratch[i] = nullptr;
+    g_ctx.scratch_words[i] = 0;
+  }
+  for (auto& kv : g_ctx.table_ws)
+    if (kv.second.first) cudaFree(kv.second.first);
+  g_ctx.table_ws.clear();
+  g_ctx.mod_cache.clear();
+  if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+  g_ctx.stream = nullptr;
+  g_ctx.ready = false;
+}
+
+uint64_t ipclb200_launch_count(void) { return g_ctx.launches.load(); }
+
+int ipclb200_modexp(const uint32_t* base, const uint32_t* exp,
+                    const uint32_t* mod, int mod_words, int exp_words,
+                    size_t count, unsigned flags, uint32_t* out) {
+  if (!base || !exp || !mod || !out)
+    return fail(IPCLB200_ERR_BAD_ARG, "modexp: null pointer");
+  if (mod_words <= 0 || exp_words <= 0)
+    return fail(IPCLB200_ERR_BAD_ARG, "modexp: non-positive width");
+  if (mod_words > IPCLB200_MAX_MOD_WORDS)
+    return fail(IPCLB200_ERR_UNSUPPORTED, "modexp: modulus wider than 8192 bits");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  return modexp_host_impl(base, exp, mod, mod_words, exp_words, count, flags, out);
+}
+
+int ipclb200_modexp_dev(const uint32_t* d_base, const uint32_t* d_exp,
+                        const uint32_t* h_mod, int mod_words, int exp_words,
+                        int exp_bits, size_t count, unsigned flags,
+                        uint32_t* d_out, void* stream) {
+  if (!d_base || !d_exp || !h_mod || !d_out)
+    return fail(IPCLB200_ERR_BAD_ARG, "modexp_dev: null pointer");
+  if (!(flags & IPCLB200_SHARED_MOD))
+    return fail(IPCLB200_ERR_UNSUPPORTED, "modexp_dev: needs IPCLB200_SHARED_MOD");
+  if (mod_words <= 0 || exp_words <= 0 || class_words(mod_words) != mod_words)
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "modexp_dev: mod_words must be one of 16,32,48,64,96,128,192,256");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  Limbs n;
+  TRY(check_modulus(h_mod, mod_words, &n));
+  std::shared_ptr<DevModulus> dm;
+  TRY(make_modulus(n, mod_words, &dm));
+  cudaStream_t s = (cudaStream_t)stream;
+  ModexpParams p{};
+  p.base = d_base;
+  p.base_stride = (flags & IPCLB200_SHARED_BASE) ? 0 : mod_words;
+  p.exp = d_exp;
+  p.exp_stride = (flags & IPCLB200_SHARED_EXP) ? 0 : exp_words;
+  p.exp_words = exp_words;
+  p.exp_bits = exp_bits > 0 ? exp_bits : exp_words * 32;
+  p.n = dm->mc.n;
+  p.rr = dm->mc.rr;
+  p.one = dm->mc.one;
+  p.n0inv = dm->d_n0inv;
+  p.out = d_out;
+  p.count = count;
+  return launch_modexp(p, mod_words, s);
+}
+
+static int modmul_common(const uint32_t* d_a, const uint32_t* d_b,
+                         const Limbs& n, int L, size_t count, unsigned flags,
+                         uint32_t* d_out, cudaStream_t s) {
+  std::shared_ptr<DevModulus> dm;
+  TRY(make_modulus(n, L, &dm));
+  ModmulParams p{};
+  p.a = d_a;
+  p.b = d_b;
+  p.b_stride = (flags & IPCLB200_SHARED_B) ? 0 : L;
+  p.m = dm->mc;
+  p.out = d_out;
+  p.count = count;
+  return launch_modmul(p, L, s);
+}
+
+int ipclb200_modmul(const uint32_t* a, const uint32_t* b, const uint32_t* mod,
+                    int mod_words, size_t count, unsigned flags, uint32_t* out) {
+  if (!a || !b || !mod || !out)
+    return fail(IPCLB200_ERR_BAD_ARG, "modmul: null pointer");
+  if (mod_words <= 0) return fail(IPCLB200_ERR_BAD_ARG, "modmul: non-positive width");
+  const int L = class_words(mod_words);
+  if (!L) return fail(IPCLB200_ERR_UNSUPPORTED, "modmul: modulus wider than 8192 bits");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  Limbs n;
+  TRY(check_modulus(mod, mod_words, &n));
+  cudaStream_t s = g_ctx.stream;
+  const bool sh_b = flags & IPCLB200_SHARED_B;
+  uint32_t *d_a, *d_b, *d_out;
+  TRY(scratch_get(0, count * (size_t)L, &d_a));
+  TRY(scratch_get(1, (sh_b ? 1 : count) * (size_t)L, &d_b));
+  TRY(scratch_get(2, count * (size_t)L, &d_out));
+  TRY(upload_padded(d_a, a, mod_words, L, count, s));
+  TRY(upload_padded(d_b, b, mod_words, L, sh_b ? 1 : count, s));
+  TRY(modmul_common(d_a, d_b, n, L, count, flags, d_out, s));
+  TRY(download_padded(out, d_out, mod_words, L, count, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int ipclb200_modmul_dev(const uint32_t* d_a, const uint32_t* d_b,
+                        const uint32_t* h_mod, int mod_words, size_t count,
+                        unsigned flags, uint32_t* d_out, void* stream) {
+  if (!d_a || !d_b || !h_mod || !d_out)
+    return fail(IPCLB200_ERR_BAD_ARG, "modmul_dev: null pointer");
+  if (mod_words <= 0 || class_words(mod_words) != mod_words)
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "modmul_dev: mod_words must be one of 16,32,48,64,96,128,192,256");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  Limbs n;
+  TRY(check_modulus(h_mod, mod_words, &n));
+  return modmul_common(d_a, d_b, n, mod_words, count, flags, d_out,
+                       (cudaStream_t)stream);
+}
+
+// ---- public key -----------------------------------------------------------
+int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs,
+                           int rand_bits, ipclb200_pubkey** out) {
+  if (!n || !out || n_words <= 0)
+    return fail(IPCLB200_ERR_BAD_ARG, "pubkey_create: bad argument");
+  if (2 * n_words > IPCLB200_MAX_MOD_WORDS)
+    return fail(IPCLB200_ERR_UNSUPPORTED, "pubkey_create: key wider than 4096 bits");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  std::unique_ptr<ipclb200_pubkey> pk(new ipclb200_pubkey);
+  pk->nl = n_words;
+  pk->n = hbn::from_words(n, n_words);
+  if (pk->n.empty()) return fail(IPCLB200_ERR_BAD_ARG, "pubkey_create: n is zero");
+  if (!(pk->n[0] & 1u))
+    return fail(IPCLB200_ERR_EVEN_MODULUS, "pubkey_create: n is even");
+  pk->nsq = hbn::mul(pk->n, pk->n);
+  pk->L = class_words(2 * n_words);
+  const int L = pk->L;
+  TRY(make_modulus(pk->nsq, L, &pk->msq));
+  // n*R mod n^2, n (exponent), hs*R mod n^2
+  Limbs R = hbn::pow2(32u * (unsigned)L);
+  Limbs nR = hbn::mod(hbn::mul(pk->n, R), pk->nsq);
+  std::vector<uint32_t> blk((size_t)L + n_words + L, 0u);
+  hbn::to_words(nR, blk.data(), L);
+  hbn::to_words(pk->n, blk.data() + 2 * L, n_words);
+  if (hs) {
+    pk->djn = true;
+    pk->rand_bits = rand_bits > 0 ? rand_bits : n_words * 16;
+    pk->hs = hbn::mod(hbn::from_words(hs, 2 * n_words), pk->nsq);
+    Limbs hsm = hbn::mod(hbn::mul(pk->hs, R), pk->nsq);
+    hbn::to_words(hsm, blk.data() + L, L);
+  }
+  CUDA_TRY(cudaMalloc(&pk->d_const, blk.size() * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(pk->d_const, blk.data(), blk.size() * sizeof(uint32_t),
+                      cudaMemcpyHostToDevice));
+  *out = pk.release();
+  return 0;
+}
+
+void ipclb200_pubkey_destroy(ipclb200_pubkey* pk) {
+  if (!pk) return;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.ready) {
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+  }
+  delete pk;
+}
+
+int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt,
+                     int pt_words, const uint32_t* r, int r_words, size_t count,
+                     int make_secure, uint32_t* ct) {
+  if (!pk || !pt || !ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt: null pointer");
+  if (make_secure && !r) return fail(IPCLB200_ERR_BAD_ARG, "encrypt: randoms missing");
+  if (pt_words <= 0 || pt_words > pk->nl)
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt: pt_words out of range");
+  if (make_secure && (r_words <= 0 || r_words > 2 * pk->nl))
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt: r_words out of range");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int L = pk->L, CW = 2 * pk->nl;
+  uint32_t *d_pt, *d_r = nullptr, *d_ct;
+  TRY(scratch_get(0, count * (size_t)pt_words, &d_pt));
+  TRY(scratch_get(2, count * (size_t)L, &d_ct));
+  CUDA_TRY(cudaMemcpyAsync(d_pt, pt, count * (size_t)pt_words * 4,
+                           cudaMemcpyHostToDevice, s));
+  int r_bits = 0;
+  if (make_secure) {
+    TRY(scratch_get(1, count * (size_t)r_words, &d_r));
+    CUDA_TRY(cudaMemcpyAsync(d_r, r, count * (size_t)r_words * 4,
+                             cudaMemcpyHostToDevice, s));
+    r_bits = max_bits(r, r_words, count, r_words);
+  }
+  TRY(encrypt_dev_impl(pk, d_pt, pt_words, d_r, r_words, r_bits, count,
+                       make_secure, d_ct, s));
+  TRY(download_padded(ct, d_ct, CW, L, count, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt,
+                         int pt_words, const uint32_t* d_r, int r_words,
+                         size_t count, int make_secure, uint32_t* d_ct,
+                         void* stream) {
+  if (!pk || !d_pt || !d_ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: null pointer");
+  if (make_secure && !d_r) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: randoms missing");
+  if (pk->L != 2 * pk->nl)
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "encrypt_dev: 2*n_words must be one of 16,32,48,64,96,128,192,256");
+  if (pt_words <= 0 || pt_words > pk->nl)
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: pt_words out of range");
+  if (make_secure && (r_words <= 0 || r_words > 2 * pk->nl))
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: r_words out of range");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  return encrypt_dev_impl(pk, d_pt, pt_words, d_r, r_words, r_words * 32, count,
+                          make_secure, d_ct, (cudaStream_t)stream);
+}
+
+// ---- private key ----------------------------------------------------------
+int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
+                            int p_words, ipclb200_privkey** out) {
+  if (!p_in || !q_in || !out || p_words <= 0)
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: bad argument");
+  if (2 * p_words > kMaxPrimeWords)
+    return fail(IPCLB200_ERR_UNSUPPORTED, "privkey_create: primes wider than 2048 bits");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  std::unique_ptr<ipclb200_privkey> sk(new ipclb200_privkey);
+  const int pl = p_words;
+  sk->pl = pl;
+  Limbs p = hbn::from_words(p_in, pl), q = hbn::from_words(q_in, pl);
+  if (hbn::cmp(q, p) < 0) p.swap(q);  // pri_key.cpp:19-22
+  if (p.empty() || !(p[0] & 1u) || !(q[0] & 1u))
+    return fail(IPCLB200_ERR_EVEN_MODULUS, "privkey_create: p and q must be odd");
+  if (hbn::cmp(p, q) == 0)
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: p and q are same");
+  sk->p = p;
+  sk->q = q;
+  sk->n = hbn::mul(p, q);
+  sk->nsq = hbn::mul(sk->n, sk->n);
+  Limbs one = hbn::from_u64(1);
+  Limbs psq = hbn::mul(p, p), qsq = hbn::mul(q, q);
+  Limbs pm1 = hbn::sub(p, one), qm1 = hbn::sub(q, one);
+  Limbs g = hbn::add(sk->n, one);
+  sk->L = class_words(2 * pl);
+  TRY(make_modulus(psq, sk->L, &sk->mp2));
+  TRY(make_modulus(qsq, sk->L, &sk->mq2));
+  TRY(make_modulus(sk->nsq, class_words(4 * pl), &sk->mnsq));
+  // computeHfun (pri_key.cpp:159-167)
+  Limbs hp, hq, pinv, tmp, lq;
+  TRY(modexp_scalar(hbn::mod(g, psq), pm1, psq, &tmp));
+  hbn::divmod(hbn::sub(tmp, one), p, &lq, nullptr);
+  if (!hbn::modinv(lq, p, &hp))
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: hp not invertible (p not prime?)");
+  TRY(modexp_scalar(hbn::mod(g, qsq), qm1, qsq, &tmp));
+  hbn::divmod(hbn::sub(tmp, one), q, &lq, nullptr);
+  if (!hbn::modinv(lq, q, &hq))
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: hq not invertible (q not prime?)");
+  if (!hbn::modinv(p, q, &pinv))
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: p not invertible mod q");
+  // lambda = lcm(p-1, q-1); mu = (L(g^lambda mod n^2))^-1 mod n (:34-37)
+  Limbs gc = hbn::gcd(pm1, qm1), lam;
+  hbn::divmod(hbn::mul(pm1, qm1), gc, &lam, nullptr);
+  sk->lambda = lam;
+  Limbs mu;
+  TRY(modexp_scalar(g, lam, sk->nsq, &tmp));
+  hbn::divmod(hbn::sub(tmp, one), sk->n, &lq, nullptr);
+  if (!hbn::modinv(lq, sk->n, &mu))
+    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: mu not invertible");
+  // constants pre-multiplied by the Montgomery radix of their modulus
+  Limbs Rp = hbn::pow2(32u * (unsigned)pl), Rn = hbn::pow2(64u * (unsigned)pl);
+  Limbs hpR = hbn::mod(hbn::mul(hp, Rp), p);
+  Limbs hqR = hbn::mod(hbn::mul(hq, Rp), q);
+  Limbs pinvR = hbn::mod(hbn::mul(pinv, Rp), q);
+  Limbs muR = hbn::mod(hbn::mul(mu, Rn), sk->n);
+  // device block: p q pm1 qm1 hpR hqR pinvR (pl each) | n muR (2pl each) |
+  // n0inv(n^2) (1, padded to 4) | lambda (2pl)
+  std::vector<uint32_t> blk(7 * (size_t)pl + 4 * (size_t)pl + 4 + 2 * (size_t)pl, 0u);
+  uint32_t* b = blk.data();
+  hbn::to_words(p, b, pl);
+  hbn::to_words(q, b + pl, pl);
+  hbn::to_words(pm1, b + 2 * pl, pl);
+  hbn::to_words(qm1, b + 3 * pl, pl);
+  hbn::to_words(hpR, b + 4 * pl, pl);
+  hbn::to_words(hqR, b + 5 * pl, pl);
+  hbn::to_words(pinvR, b + 6 * pl, pl);
+  hbn::to_words(sk->n, b + 7 * pl, 2 * pl);
+  hbn::to_words(muR, b + 9 * pl, 2 * pl);
+  b[11 * pl] = sk->mnsq->mc.n0inv;
+  hbn::to_words(lam, b + 11 * pl + 4, 2 * pl);
+  CUDA_TRY(cudaMalloc(&sk->d_const, blk.size() * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(sk->d_const, blk.data(), blk.size() * sizeof(uint32_t),
+                      cudaMemcpyHostToDevice));
+  const uint32_t* d = sk->d_const;
+  sk->d_p = d;
+  sk->d_q = d + pl;
+  sk->d_pm1 = d + 2 * pl;
+  sk->d_qm1 = d + 3 * pl;
+  sk->d_hpR = d + 4 * pl;
+  sk->d_hqR = d + 5 * pl;
+  sk->d_pinvR = d + 6 * pl;
+  sk->d_n = d + 7 * pl;
+  sk->d_muR = d + 9 * pl;
+  sk->d_lambda = d + 11 * pl + 4;
+  sk->p_n0inv = hbn::neg_inv32(p[0]);
+  sk->q_n0inv = hbn::neg_inv32(q[0]);
+  sk->n_n0inv = hbn::neg_inv32(sk->n[0]);
+  sk->p_inv32 = 0u - sk->p_n0inv;
+  sk->q_inv32 = 0u - sk->q_n0inv;
+  sk->n_inv32 = 0u - sk->n_n0inv;
+  sk->pm1_bits = hbn::bitlen(pm1);
+  sk->qm1_bits = hbn::bitlen(qm1);
+  sk->lambda_bits = hbn::bitlen(lam);
+  *out = sk.release();
+  return 0;
+}
+
+void ipclb200_privkey_destroy(ipclb200_privkey* sk) {
+  if (!sk) return;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.ready) {
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+  }
+  delete sk;
+}
+
+int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct,
+                     size_t count, int use_crt, uint32_t* pt) {
+  if (!sk || !ct || !pt) return fail(IPCLB200_ERR_BAD_ARG, "decrypt: null pointer");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int pl = sk->pl;
+  const int CW = 4 * pl;  // caller's ciphertext words
+  uint32_t *d_ct, *d_x, *d_pt;
+  // the kernels read a ciphertext as 2L (CRT, L = class of p^2) or L (RAW,
+  // L = class of n^2) words; zero padding keeps the value
+  const int ctw = use_crt ? 2 * sk->L : sk->mnsq->L;
+  const int xw = use_crt ? 2 * sk->L : sk->mnsq->L;
+  TRY(scratch_get(0, count * (size_t)ctw, &d_ct));
+  TRY(scratch_get(1, count * (size_t)xw, &d_x));
+  TRY(scratch_get(2, count * (size_t)(2 * pl), &d_pt));
+  TRY(upload_padded(d_ct, ct, CW, ctw, count, s));
+  TRY(decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, s));
+  CUDA_TRY(cudaMemcpyAsync(pt, d_pt, count * (size_t)(2 * pl) * 4,
+                           cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
+                         size_t count, int use_crt, uint32_t* d_pt,
+                         void* stream) {
+  if (!sk || !d_ct || !d_pt) return fail(IPCLB200_ERR_BAD_ARG, "decrypt_dev: null pointer");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  const int pl = sk->pl;
+  if ((use_crt && sk->L != 2 * pl) || (!use_crt && sk->mnsq->L != 4 * pl))
+    return fail(IPCLB200_ERR_UNSUPPORTED, "decrypt_dev: key width is not a kernel size class");
+  uint32_t* d_x;
+  TRY(scratch_get(6, count * (size_t)(4 * pl), &d_x));
+  return decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, (cudaStream_t)stream);
+}
+
+// ---- measurement ----------------------------------------------------------
+int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int threads = 256, blocks = g_ctx.sms * 8;
+  uint32_t* d_out;
+  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    CUDA_TRY(cudaEventRecord(a, s));
+    int_peak_kernel<<<blocks, threads, 0, s>>>(d_out, 3u + rep, 5u);
+    CUDA_TRY(cudaEventRecord(b, s));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  g_ctx.launches += 6;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  double macs = (double)threads * blocks * kPeakIters * 16.0;
+  if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_ctx.device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// kernels.cuh -- the batch kernels of the B200 Paillier hot path.
+//
+// Work decomposition (all kernels): one big integer = one group of T lanes,
+// 32/T groups per warp, persistent grid: group g handles elements g, g+G,
+// g+2G, ... so that consecutive groups touch consecutive elements (coalesced
+// 128-bit loads/stores of the batch) and every warp runs the same trip count.
+// Per-group scratch (the window table) lives in a workspace slot indexed by the
+// group id, so it is sized by the number of resident groups -- it stays in L2 --
+// not by the batch.
+#pragma once
+#include <cstdint>
+
+#include "mont_core.cuh"
+
+namespace ipclb200 {
+
+constexpr int kBlockThreads = 128;
+constexpr int kMaxWindow = 6;
+
+// Per-modulus constants in device memory, each an array of L words.
+struct ModConst {
+  const uint32_t* n;    // the modulus
+  const uint32_t* rr;   // R^2 mod n
+  const uint32_t* r3;   // R^3 mod n
+  const uint32_t* one;  // R mod n   (Montgomery form of 1)
+  uint32_t n0inv;       // -n^-1 mod 2^32
+  uint32_t small_mod;   // n < R/4: canonicalise through two multiplies
+};
+
+// window `k` (w bits wide) of an exponent of `ew` words
+__device__ __forceinline__ uint32_t exp_window(const uint32_t* __restrict__ e,
+                                               int ew, int k, int w) {
+  int bit = k * w;
+  int wi = bit >> 5, sh = bit & 31;
+  uint32_t lo = (wi < ew) ? __ldg(e + wi) : 0u;
+  uint32_t hi = (wi + 1 < ew) ? __ldg(e + wi + 1) : 0u;
+  uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+// Fixed-window exponentiation of one group.  xm: base in Montgomery form.
+// Leaves acc = base^e in Montgomery form (almost reduced).  tab: this group's
+// (1<<w)*L-word scratch.  Table loads for the next window are issued before
+// the w squarings so their latency is covered.
+template <int K, int T>
+__device__ __forceinline__ void modexp_core(
+    uint32_t (&acc)[K], const uint32_t (&xm)[K], const uint32_t (&n)[K],
+    uint32_t n0inv, const uint32_t* __restrict__ one,
+    const uint32_t* __restrict__ e, int ew, int ebits, int w,
+    uint32_t* __restrict__ tab) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  {
+    uint32_t t[K];
+    M::load(t, one);
+    M::store(tab, t);
+    M::store(tab + L, xm);
+#pragma unroll
+    for (int j = 0; j < K; j++) t[j] = xm[j];
+    for (int i = 2; i < (1 << w); i++) {
+      M::mul(t, t, xm, n, n0inv);
+      M::store(tab + (size_t)i * L, t);
+    }
+  }
+  int nwin = (ebits + w - 1) / w;
+  if (nwin < 1) nwin = 1;
+  M::load(acc, tab + (size_t)exp_window(e, ew, nwin - 1, w) * L);
+  for (int k = nwin - 2; k >= 0; k--) {
+    uint32_t t[K];
+    M::load(t, tab + (size_t)exp_window(e, ew, k, w) * L);
+    // w squarings then the table multiply, through ONE inlined copy of the
+    // multiply so the hot loop stays inside the instruction cache
+#pragma unroll 1
+    for (int s = 0; s <= w; s++) {
+      uint32_t b[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) b[j] = (s == w) ? t[j] : acc[j];
+      M::mul(acc, acc, b, n, n0inv);
+    }
+  }
+}
+
+// x (< R, any residue class) -> canonical x mod n
+template <int K, int T>
+__device__ __forceinline__ void canonicalize(uint32_t (&x)[K],
+                                             const uint32_t (&n)[K],
+                                             uint32_t n0inv,
+                                             const uint32_t* __restrict__ rr,
+                                             uint32_t small_mod) {
+  using M = Mont<K, T>;
+  if (small_mod) {
+    uint32_t t[K];
+    M::load(t, rr);
+    M::mul(x, x, t, n, n0inv);
+    M::from_mont(x, x, n, n0inv);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) M::sub_n_if_ge(x, n);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K1: generic batched modexp  (ipcl::ippModExp, ipcl/mod_exp.cpp:655-678)
+// --------------------------------------------------------------------------
+struct ModexpParams {
+  const uint32_t* base;
+  size_t base_stride;  // words, 0 = shared
+  const uint32_t* exp;
+  size_t exp_stride;  // words, 0 = shared
+  int exp_words;
+  int exp_bits;
+  // modulus constants: shared (stride 0) or per element (stride L / 1)
+  const uint32_t* n;
+  const uint32_t* rr;
+  const uint32_t* one;
+  const uint32_t* n0inv;
+  size_t mod_stride;
+  size_t n0_stride;
+  uint32_t* out;
+  size_t count;
+  uint32_t* table_ws;
+  int window;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    modexp_kernel(const ModexpParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  const size_t ngroups = (size_t)gridDim.x * gpb;
+  uint32_t* tab = p.table_ws + gid * ((size_t)L << p.window);
+  const size_t iters = (p.count + ngroups - 1) / ngroups;
+  for (size_t it = 0; it < iters; it++) {
+    const size_t inst = it * ngroups + gid;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    uint32_t n[K], x[K], acc[K];
+    M::load(n, p.n + ii * p.mod_stride);
+    const uint32_t n0inv = __ldg(p.n0inv + ii * p.n0_stride);
+    {
+      uint32_t rr[K];
+      M::load(rr, p.rr + ii * p.mod_stride);
+      M::load(x, p.base + ii * p.base_stride);
+      M::mul(x, x, rr, n, n0inv);
+    }
+    modexp_core<K, T>(acc, x, n, n0inv, p.one + ii * p.mod_stride,
+                      p.exp + ii * p.exp_stride, p.exp_words, p.exp_bits,
+                      p.window, tab);
+    M::from_mont(x, acc, n, n0inv);
+    if (valid) M::store(p.out + inst * L, x);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K2: batched modular multiply  (CipherText::raw_add, ciphertext.cpp:135-141)
+// --------------------------------------------------------------------------
+struct ModmulParams {
+  const uint32_t* a;
+  const uint32_t* b;
+  size_t b_stride;  // 0 = shared
+  ModConst m;
+  uint32_t* out;
+  size_t count;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    modmul_kernel(const ModmulParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  const size_t ngroups = (size_t)gridDim.x * gpb;
+  const size_t iters = (p.count + ngroups - 1) / ngroups;
+  uint32_t n[K], rr[K];
+  M::load(n, p.m.n);
+  M::load(rr, p.m.rr);
+  for (size_t it = 0; it < iters; it++) {
+    const size_t inst = it * ngroups + gid;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    uint32_t a[K], b[K];
+    M::load(a, p.a + ii * L);
+    M::load(b, p.b + ii * p.b_stride);
+    M::mul(a, a, rr, n, p.m.n0inv);  // a*R
+    M::mul(a, a, b, n, p.m.n0inv);   // a*b  (< R)
+    canonicalize<K, T>(a, n, p.m.n0inv, p.m.rr, p.m.small_mod);
+    if (valid) M::store(p.out + inst * L, a);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K3: fused Paillier encrypt  (PublicKey::raw_encrypt + applyObfuscator,
+//     ipcl/pub_key.cpp:51-110), modulus n^2 of L = 2*NL words.
+//   gm  = n*pt + 1            (one multiply by n*R mod n^2, then +1)
+//   obf = hs^r  (DJN: fixed-base comb table, no squarings -- K5)
+//       | r^n   (non-DJN: fixed-window modexp, shared exponent n)
+//   ct  = obf * gm mod n^2    (obf stays in Montgomery form, so this multiply
+//                              also leaves Montgomery form)
+// --------------------------------------------------------------------------
+struct EncryptParams {
+  const uint32_t* pt;
+  int pt_words;
+  const uint32_t* r;
+  int r_words;
+  int r_bits;
+  ModConst m;           // n^2
+  const uint32_t* nR;   // n * R mod n^2
+  const uint32_t* n_exp;  // n as exponent (non-DJN), NL words
+  int n_exp_words;
+  const uint32_t* hs_m;  // hs in Montgomery form (DJN generic path), L words
+  const uint32_t* comb;  // comb table [nwin][1<<cw][L] or nullptr
+  int comb_w;
+  int comb_windows;
+  int mode;  // 0: no obfuscator, 1: DJN comb, 2: DJN generic window, 3: non-DJN
+  uint32_t* ct;
+  size_t count;
+  uint32_t* table_ws;
+  int window;
+};
+
+// load `words` words (zero extended to L) spread over the group
+template <int K, int T>
+__device__ __forceinline__ void load_padded(uint32_t (&x)[K],
+                                            const uint32_t* __restrict__ p,
+                                            int words) {
+  const int base = Mont<K, T>::lane_t() * K;
+#pragma unroll
+  for (int j = 0; j < K; j++) x[j] = (base + j < words) ? p[base + j] : 0u;
+}
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    encrypt_kernel(const EncryptParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  const size_t ngroups = (size_t)gridDim.x * gpb;
+  uint32_t* tab = p.table_ws + gid * ((size_t)L << p.window);
+  const size_t iters = (p.count + ngroups - 1) / ngroups;
+  uint32_t n[K];
+  M::load(n, p.m.n);
+  const uint32_t n0inv = p.m.n0inv;
+  for (size_t it = 0; it < iters; it++) {
+    const size_t inst = it * ngroups + gid;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    uint32_t gm[K];
+    {
+      uint32_t t[K];
+      load_padded<K, T>(gm, p.pt + ii * (size_t)p.pt_words, p.pt_words);
+      M::load(t, p.nR);
+      M::mul(gm, gm, t, n, n0inv);  // n*pt mod n^2 (< R)
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = 0;
+      uint32_t c = M::group_add(gm, t, 1u);  // + 1
+      if (__any_sync(IPCLB200_FULL_MASK, c)) M::cond_sub_n(gm, n, c);
+    }
+    if (p.mode == 0) {
+      canonicalize<K, T>(gm, n, n0inv, p.m.rr, p.m.small_mod);
+      if (valid) M::store(p.ct + inst * L, gm);
+      continue;
+    }
+    uint32_t acc[K];
+    if (p.mode == 1) {
+      const uint32_t* e = p.r + ii * (size_t)p.r_words;
+      const size_t wstride = (size_t)L << p.comb_w;
+      M::load(acc, p.comb + (size_t)exp_window(e, p.r_words, 0, p.comb_w) * L);
+      uint32_t t[K];
+      if (p.comb_windows > 1)
+        M::load(t, p.comb + wstride +
+                       (size_t)exp_window(e, p.r_words, 1, p.comb_w) * L);
+      for (int k = 1; k < p.comb_windows; k++) {
+        uint32_t tn[K];
+        if (k + 1 < p.comb_windows)
+          M::load(tn, p.comb + (size_t)(k + 1) * wstride +
+                          (size_t)exp_window(e, p.r_words, k + 1, p.comb_w) * L);
+        M::mul(acc, acc, t, n, n0inv);
+#pragma unroll
+        for (int j = 0; j < K; j++) t[j] = tn[j];
+      }
+    } else if (p.mode == 2) {
+      uint32_t x[K];
+      M::load(x, p.hs_m);
+      modexp_core<K, T>(acc, x, n, n0inv, p.m.one,
+                        p.r + ii * (size_t)p.r_words, p.r_words, p.r_bits,
+                        p.window, tab);
+    } else {
+      uint32_t x[K], t[K];
+      load_padded<K, T>(x, p.r + ii * (size_t)p.r_words, p.r_words);
+      M::load(t, p.m.rr);
+      M::mul(x, x, t, n, n0inv);
+      modexp_core<K, T>(acc, x, n, n0inv, p.m.one, p.n_exp, p.n_exp_words,
+                        p.n_exp_words * 32, p.window, tab);
+    }
+    M::mul(acc, acc, gm, n, n0inv);  // obf*gm, out of Montgomery form
+    canonicalize<K, T>(acc, n, n0inv, p.m.rr, p.m.small_mod);
+    if (valid) M::store(p.ct + inst * L, acc);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K5: fixed-base comb table for the DJN obfuscator hs^r (pub_key.cpp:51-64:
+//     the same base hs for every element).  comb[i][j] = hs^(j * 2^(w*i)) in
+//     Montgomery form.  Phase A (one group): the spine g_i = hs^(2^(w*i)).
+//     Phase B (one group per window): the 2^w multiples of g_i.
+// --------------------------------------------------------------------------
+struct CombParams {
+  ModConst m;
+  const uint32_t* hs_m;  // hs in Montgomery form
+  uint32_t* comb;
+  int w;
+  int windows;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(32) comb_spine_kernel(const CombParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  // every group of the single warp computes the same spine; group 0 stores
+  uint32_t n[K], g[K];
+  M::load(n, p.m.n);
+  M::load(g, p.hs_m);
+  const bool writer = (threadIdx.x / T) == 0;
+  const size_t wstride = (size_t)L << p.w;
+  for (int i = 0; i < p.windows; i++) {
+    if (writer) M::store(p.comb + (size_t)i * wstride + L, g);
+    for (int s = 0; s < p.w; s++) M::mul(g, g, g, n, p.m.n0inv);
+  }
+}
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    comb_fill_kernel(const CombParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const int gpb = blockDim.x / T;
+  const int gid = blockIdx.x * gpb + threadIdx.x / T;
+  const bool valid = gid < p.windows;
+  const int i = valid ? gid : p.windows - 1;
+  uint32_t* row = p.comb + (size_t)i * ((size_t)L << p.w);
+  uint32_t n[K], g[K], t[K];
+  M::load(n, p.m.n);
+  M::load(g, row + L);
+  M::load(t, p.m.one);
+  if (valid) M::store(row, t);
+#pragma unroll
+  for (int j = 0; j < K; j++) t[j] = g[j];
+  for (int j = 2; j < (1 << p.w); j++) {
+    M::mul(t, t, g, n, p.m.n0inv);
+    if (valid) M::store(row + (size_t)j * L, t);
+  }
+}
+
+// x -> x*R mod n elementwise (used to put hs into Montgomery form)
+template <int K, int T>
+__global__ void __launch_bounds__(32)
+    to_mont_kernel(const ModConst m, const uint32_t* x, uint32_t* out) {
+  using M = Mont<K, T>;
+  uint32_t n[K], a[K], rr[K];
+  M::load(n, m.n);
+  M::load(rr, m.rr);
+  M::load(a, x);
+  M::mul(a, a, rr, n, m.n0inv);
+  if ((threadIdx.x / T) == 0) M::store(out, a);
+}
+
+// --------------------------------------------------------------------------
+// K4: fused CRT decrypt, modexp part  (PrivateKey::decryptCRT,
+//     ipcl/pri_key.cpp:114-146).  Two tasks per ciphertext (mod p^2, mod q^2),
+//     L = words of p^2.  Prologue: ct mod p^2 by one Montgomery reduction of
+//     the low half plus the high half; then x = ct^(p-1) mod p^2, canonical.
+//     The L-function / hp / CRT recombination runs in crt_finish_kernel.
+// --------------------------------------------------------------------------
+struct DecryptCrtParams {
+  const uint32_t* ct;  // count x 2L words
+  ModConst m[2];       // p^2, q^2
+  const uint32_t* e[2];  // p-1, q-1
+  int e_words;
+  int e_bits[2];
+  uint32_t* x;  // out: count x 2 x L words
+  size_t count;
+  uint32_t* table_ws;
+  int window;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    decrypt_crt_kernel(const DecryptCrtParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  const size_t ngroups = (size_t)gridDim.x * gpb;
+  uint32_t* tab = p.table_ws + gid * ((size_t)L << p.window);
+  const size_t ntask = p.count * 2;
+  const size_t iters = (ntask + ngroups - 1) / ngroups;
+  // ngroups is even, so a group keeps its side for every iteration
+  const int side = (int)(gid & 1);
+  const ModConst m = p.m[side];
+  uint32_t n[K];
+  M::load(n, m.n);
+  const int ebits = max(p.e_bits[0], p.e_bits[1]);
+  for (size_t it = 0; it < iters; it++) {
+    const size_t task = it * ngroups + gid;
+    const bool valid = task < ntask;
+    const size_t tt = valid ? task : ntask - 2 + side;
+    const uint32_t* c = p.ct + (tt >> 1) * (size_t)(2 * L);
+    uint32_t x[K], acc[K];
+    {
+      uint32_t lo[K], hi[K], t[K];
+      M::load(lo, c);
+      M::load(hi, c + L);
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = 0;
+      if (M::lane_t() == 0) t[0] = 1;
+      M::mul(lo, lo, t, n, m.n0inv);  // lo * R^-1   (<= n)
+      uint32_t cy = M::group_add(lo, hi, 0u);  // ct * R^-1 mod n, < R + n
+      if (__any_sync(IPCLB200_FULL_MASK, cy)) M::cond_sub_n(lo, n, cy);
+      M::load(t, m.r3);
+      M::mul(x, lo, t, n, m.n0inv);  // ct * R mod n: Montgomery form
+    }
+    modexp_core<K, T>(acc, x, n, m.n0inv, m.one, p.e[side], p.e_words, ebits,
+                      p.window, tab);
+    M::from_mont(x, acc, n, m.n0inv);
+    if (valid) M::store(p.x + task * L, x);
+  }
+}
+
+// --------------------------------------------------------------------------
+// CRT recombination, one thread per ciphertext (tiny next to the modexps:
+// ~8k MAC32 against ~20M).  pri_key.cpp:141-157:
+//   dp = L_p(xp) * hp mod p,  dq = L_q(xq) * hq mod q,  L_a(x) = (x-1)/a
+//   pt = dp + ((dq - dp) * p^-1 mod q) * p
+// Exact division by the odd prime is a multiplication by its inverse mod
+// 2^32 limb by limb; the two modular products are word-serial Montgomery
+// multiplies against constants pre-multiplied by R.
+// --------------------------------------------------------------------------
+constexpr int kMaxPrimeWords = 128;  // words of n for the RAW tail, 2x a prime
+
+struct CrtFinishParams {
+  const uint32_t* x;  // count x 2 x (2*PL) words: xp, xq
+  const uint32_t* p;  // PL words
+  const uint32_t* q;
+  const uint32_t* hpR;    // hp * Rp mod p
+  const uint32_t* hqR;    // hq * Rq mod q
+  const uint32_t* pinvR;  // (p^-1 mod q) * Rq mod q
+  uint32_t p_inv32;       // p^-1 mod 2^32   (exact division)
+  uint32_t q_inv32;
+  uint32_t p_n0inv;  // -p^-1 mod 2^32  (Montgomery)
+  uint32_t q_n0inv;
+  int pl;
+  int xl;        // words per residue in x (the kernel size class of p^2)
+  uint32_t* pt;  // count x 2*PL words
+  size_t count;
+};
+
+// q[0..pl) = (x - 1) / d for x = 1 (mod d), x < d^2; x has 2*pl words
+__device__ inline void exact_div_minus1(uint32_t* q, const uint32_t* x,
+                                        const uint32_t* d, uint32_t dinv32,
+                                        int pl) {
+  uint32_t t[kMaxPrimeWords];
+  // t = low pl words of x - 1 (the quotient only depends on them)
+  uint32_t borrow = 1;
+  for (int i = 0; i < pl; i++) {
+    uint32_t v = x[i];
+    t[i] = v - borrow;
+    borrow = (v < borrow) ? 1u : 0u;
+  }
+  for (int i = 0; i < pl; i++) {
+    uint32_t qi = t[i] * dinv32;
+    q[i] = qi;
+    // t -= qi * d << (32 i), only words < pl matter
+    uint64_t carry = 0;
+    uint32_t br = 0;
+    for (int j = 0; i + j < pl; j++) {
+      uint64_t pr = (uint64_t)qi * d[j] + carry;
+      carry = pr >> 32;
+      uint32_t sub = (uint32_t)pr;
+      uint32_t v = t[i + j];
+      uint32_t r1 = v - sub;
+      uint32_t b1 = v < sub;
+      uint32_t r2 = r1 - br;
+      uint32_t b2 = r1 < br;
+      t[i + j] = r2;
+      br = b1 | b2;
+    }
+  }
+}
+
+// r = a * b * R^-1 mod m (canonical), word-serial CIOS, pl words
+__device__ inline void mont_mul_serial(uint32_t* r, const uint32_t* a,
+                                       const uint32_t* b, const uint32_t* m,
+                                       uint32_t n0inv, int pl) {
+  uint32_t t[kMaxPrimeWords + 2];
+  for (int i = 0; i < pl + 2; i++) t[i] = 0;
+  for (int i = 0; i < pl; i++) {
+    uint64_t c = 0;
+    uint32_t bi = b[i];
+    for (int j = 0; j < pl; j++) {
+      c += (uint64_t)a[j] * bi + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[pl];
+    t[pl] = (uint32_t)c;
+    t[pl + 1] = (uint32_t)(c >> 32);
+    uint32_t qd = t[0] * n0inv;
+    c = ((uint64_t)qd * m[0] + t[0]) >> 32;
+    for (int j = 1; j < pl; j++) {
+      c += (uint64_t)qd * m[j] + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[pl];
+    t[pl - 1] = (uint32_t)c;
+    t[pl] = t[pl + 1] + (uint32_t)(c >> 32);
+  }
+  // canonical: t < 2m
+  bool ge = t[pl] != 0;
+  if (!ge) {
+    ge = true;
+    for (int i = pl - 1; i >= 0; i--) {
+      if (t[i] != m[i]) {
+        ge = t[i] > m[i];
+        break;
+      }
+    }
+  }
+  uint32_t br = 0;
+  for (int i = 0; i < pl; i++) {
+    uint32_t s = ge ? m[i] : 0u;
+    uint32_t v = t[i];
+    uint32_t r1 = v - s;
+    uint32_t b1 = v < s;
+    uint32_t r2 = r1 - br;
+    uint32_t b2 = r1 < br;
+    r[i] = r2;
+    br = b1 | b2;
+  }
+}
+
+__global__ void crt_finish_kernel(const CrtFinishParams p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.count) return;
+  const int pl = p.pl;
+  const uint32_t* xp = p.x + i * (size_t)(2 * p.xl);
+  const uint32_t* xq = xp + p.xl;
+  uint32_t l[kMaxPrimeWords], dp[kMaxPrimeWords], dq[kMaxPrimeWords];
+  exact_div_minus1(l, xp, p.p, p.p_inv32, pl);
+  mont_mul_serial(dp, l, p.hpR, p.p, p.p_n0inv, pl);
+  exact_div_minus1(l, xq, p.q, p.q_inv32, pl);
+  mont_mul_serial(dq, l, p.hqR, p.q, p.q_n0inv, pl);
+  // l = (dq - dp) mod q   (dp < p < q)
+  uint32_t br = 0;
+  for (int j = 0; j < pl; j++) {
+    uint32_t v = dq[j], s = dp[j];
+    uint32_t r1 = v - s;
+    uint32_t b1 = v < s;
+    uint32_t r2 = r1 - br;
+    uint32_t b2 = r1 < br;
+    l[j] = r2;
+    br = b1 | b2;
+  }
+  if (br) {
+    uint64_t c = 0;
+    for (int j = 0; j < pl; j++) {
+      c += (uint64_t)l[j] + p.q[j];
+      l[j] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  uint32_t u[kMaxPrimeWords];
+  mont_mul_serial(u, l, p.pinvR, p.q, p.q_n0inv, pl);
+  // pt = dp + u * p   (2*pl words, < n)
+  uint32_t o[kMaxPrimeWords];
+  for (int j = 0; j < 2 * pl; j++) o[j] = (j < pl) ? dp[j] : 0u;
+  for (int a = 0; a < pl; a++) {
+    uint64_t c = 0;
+    uint32_t ua = u[a];
+    for (int j = 0; j < pl; j++) {
+      c += (uint64_t)ua * p.p[j] + o[a + j];
+      o[a + j] = (uint32_t)c;
+      c >>= 32;
+    }
+    for (int j = a + pl; c && j < 2 * pl; j++) {
+      c += o[j];
+      o[j] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  uint32_t* dst = p.pt + i * (size_t)(2 * pl);
+  for (int j = 0; j < 2 * pl; j++) dst[j] = o[j];
+}
+
+// decryptRAW tail, one thread per ciphertext (pri_key.cpp:105-110):
+//   pt = ((x - 1) / n) * mu mod n     with x = ct^lambda mod n^2
+struct RawFinishParams {
+  const uint32_t* x;  // count x 2*NL words
+  const uint32_t* n;  // NL words
+  const uint32_t* muR;  // mu * Rn mod n
+  uint32_t n_inv32;
+  uint32_t n_n0inv;
+  int nl;
+  int xl;  // words per element of x
+  uint32_t* pt;
+  size_t count;
+};
+
+__global__ void raw_finish_kernel(const RawFinishParams p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.count) return;
+  uint32_t l[kMaxPrimeWords];
+  exact_div_minus1(l, p.x + i * (size_t)p.xl, p.n, p.n_inv32, p.nl);
+  mont_mul_serial(p.pt + i * (size_t)p.nl, l, p.muR, p.n, p.n_n0inv, p.nl);
+}
+
+// --------------------------------------------------------------------------
+// Integer-pipe peak: carry-dependent IMAD.WIDE.U32 chains, the exact
+// instruction the Montgomery rows are made of.
+// --------------------------------------------------------------------------
+constexpr int kPeakIters = 2048;
+__global__ void int_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t e[17], o[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) {
+    e[i] = threadIdx.x + i;
+    o[i] = threadIdx.x * 3 + i;
+  }
+  uint32_t x = a + threadIdx.x, y = b;
+  for (int it = 0; it < kPeakIters; it++) {
+    mad_lo_cc(e[0], x, y, e[0]);
+    madc_hi_cc(e[1], x, y, e[1]);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+      madc_lo_cc(e[i], x, y, e[i]);
+      madc_hi_cc(e[i + 1], x, y, e[i + 1]);
+    }
+    addc(e[16], e[16], 0);
+    mad_lo_cc(o[0], y, x, o[0]);
+    madc_hi_cc(o[1], y, x, o[1]);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+      madc_lo_cc(o[i], y, x, o[i]);
+      madc_hi_cc(o[i + 1], y, x, o[i + 1]);
+    }
+    addc(o[16], o[16], 0);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 17; i++) s ^= e[i] ^ o[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace ipclb200

@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the golden
+fixtures and the reference's ISO/IEC 18033-6 known-answer vectors.  Bit-exact:
+integer work, no tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+from pailliercryptolib_b200.limbs import (batch_from_limbs, batch_to_limbs,
+                                          from_limbs, random_limbs, to_limbs)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_modexp_golden_vectors(capi, modexp_vectors):
+    """every golden vector, one modulus per call group (heterogeneous path)"""
+    by_bits = {}
+    for v in modexp_vectors:
+        by_bits.setdefault(v["bits"], []).append(v)
+    for bits, vs in by_bits.items():
+        L = bits // 32
+        b = batch_to_limbs([int(v["b"], 16) for v in vs], L)
+        e = batch_to_limbs([int(v["e"], 16) for v in vs], L)
+        m = batch_to_limbs([int(v["m"], 16) for v in vs], L)
+        r = capi.modexp(b, e, m, 0)
+        assert batch_from_limbs(r) == [int(v["r"], 16) for v in vs], bits
+
+
+@pytest.mark.parametrize("bits", [512, 1024, 1536, 2048, 3072, 4096, 6144, 8192])
+def test_modexp_random_vs_oracle(capi, oracle, bits):
+    """shared odd modulus with the top bit set, per-element base and exponent;
+    batch sizes that are not multiples of the group count"""
+    L = bits // 32
+    rng = np.random.default_rng(bits)
+    count = {512: 1500, 1024: 700, 1536: 300, 2048: 301, 3072: 100, 4096: 67,
+             6144: 21, 8192: 9}[bits]
+    mod = random_limbs(rng, 1, L)
+    mod[0, 0] |= 1
+    mod[0, -1] |= 0x80000000
+    base = random_limbs(rng, count, L)          # includes bases >= modulus
+    ebits_words = max(1, L // 2)
+    exp = random_limbs(rng, count, ebits_words)
+    got = capi.modexp(base, exp, mod, capi.SHARED_MOD)
+    want = oracle.modexp(base, exp, mod, shared_mod=True)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("words", [1, 7, 16, 20, 33, 40, 65, 100, 129])
+def test_modexp_unaligned_widths(capi, oracle, words):
+    """moduli whose width is not a kernel size class are zero padded"""
+    rng = np.random.default_rng(words)
+    count = 37
+    mod = random_limbs(rng, 1, words, top_mask=0x0FFFFFFF)
+    mod[0, 0] |= 1
+    mod[0, -1] |= 0x01000000
+    base = random_limbs(rng, count, words)
+    exp = random_limbs(rng, count, 3)
+    got = capi.modexp(base, exp, mod, capi.SHARED_MOD)
+    want = oracle.modexp(base, exp, mod, shared_mod=True)
+    assert np.array_equal(got, want)
+
+
+def test_modexp_shared_operands(capi, oracle):
+    rng = np.random.default_rng(7)
+    L, count = 64, 50
+    mod = random_limbs(rng, 1, L)
+    mod[0, 0] |= 1
+    base1 = random_limbs(rng, 1, L)
+    exp1 = random_limbs(rng, 1, 8)
+    base = random_limbs(rng, count, L)
+    exp = random_limbs(rng, count, 8)
+    got = capi.modexp(base1, exp, mod, capi.SHARED_MOD | capi.SHARED_BASE)
+    want = oracle.modexp(base1, exp, mod, shared_mod=True, shared_base=True)
+    assert np.array_equal(got, want)
+    got = capi.modexp(base, exp1, mod, capi.SHARED_MOD | capi.SHARED_EXP)
+    want = oracle.modexp(base, exp1, mod, shared_mod=True, shared_exp=True)
+    assert np.array_equal(got, want)
+
+
+def test_modexp_edge_exponents_and_batch_one(capi):
+    L = 32
+    m = (1 << 1023) + 1155
+    mod = batch_to_limbs([m], L)
+    for b, e in [(5, 0), (0, 0), (0, 5), (1, 12345), (m - 1, 2), (m - 1, 3),
+                 (m + 7, 3), (2, 1 << 100)]:
+        got = capi.modexp(batch_to_limbs([b], L), batch_to_limbs([e], 4), mod,
+                          capi.SHARED_MOD)
+        assert from_limbs(got[0]) == pow(b, e, m), (b, e)
+    one = batch_to_limbs([1], L)
+    got = capi.modexp(batch_to_limbs([5], L), batch_to_limbs([3], 1), one,
+                      capi.SHARED_MOD)
+    assert from_limbs(got[0]) == 0
+
+
+def test_modexp_errors(capi):
+    L = 16
+    b = batch_to_limbs([3], L)
+    with pytest.raises(capi.IpclB200Error) as ei:
+        capi.modexp(b, b, batch_to_limbs([10], L), capi.SHARED_MOD)
+    assert ei.value.code == -2
+    with pytest.raises(capi.IpclB200Error) as ei:
+        capi.modexp(b, b, batch_to_limbs([0], L), capi.SHARED_MOD)
+    assert ei.value.code == -1
+    # empty batch is a no-op
+    out = capi.modexp(np.zeros((0, L), np.uint32), np.zeros((0, L), np.uint32),
+                      batch_to_limbs([7], L), capi.SHARED_MOD)
+    assert out.shape[0] <= 1
+
+
+@pytest.mark.parametrize("bits", [1024, 2048, 4096, 6144])
+def test_modmul_vs_oracle(capi, oracle, bits):
+    L = bits // 32
+    rng = np.random.default_rng(bits + 1)
+    count = 333
+    for top in (0x80000000, 0x00000001):       # large and "small" modulus
+        mod = random_limbs(rng, 1, L, top_mask=(top << 1) - 1 if top > 1 else 1)
+        mod[0, 0] |= 1
+        mod[0, -1] |= top
+        a = random_limbs(rng, count, L)
+        b = random_limbs(rng, count, L)
+        got = capi.modmul(a, b, mod[0])
+        want = oracle.modmul(a, b, mod[0])
+        assert np.array_equal(got, want)
+        got = capi.modmul(a, b[0:1], mod[0], capi.SHARED_B)
+        want = oracle.modmul(a, b[0:1], mod[0], b_shared=True)
+        assert np.array_equal(got, want)
+
+
+def test_iso_kat_through_cabi(capi, iso):
+    """The reference's only known-answer test, replayed through the C ABI:
+    test_cryptography.cpp:198-240 (21 values, non-DJN key, injected r)."""
+    p, q = iso["p"], iso["q"]
+    n = p * q
+    pk = capi.PubKey(to_limbs(n, 64))
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    ms = [iso["m0"]] * 21
+    rs = [iso["r0"]] * 21
+    ms[1], rs[1] = iso["m1"], iso["r1"]
+    ct = pk.encrypt(batch_to_limbs(ms, 64), batch_to_limbs(rs, 64))
+    got = batch_from_limbs(ct)
+    assert got[0] == iso["c1"]
+    assert got[1] == iso["c2"]
+    assert batch_from_limbs(sk.decrypt(ct)) == ms
+    s = capi.modmul(ct[0:1], ct[1:2], to_limbs(n * n, 128))
+    assert from_limbs(s[0]) == iso["c1c2"]
+    assert from_limbs(sk.decrypt(s)[0]) == iso["m1m2"]
+    assert from_limbs(sk.decrypt(s, use_crt=False)[0]) == iso["m1m2"]
+
+
+@pytest.mark.parametrize("bits", ["1024", "2048", "3072"])
+def test_scheme_golden_through_cabi(capi, keys, scheme_vectors, bits, monkeypatch):
+    k = keys[bits]
+    items = scheme_vectors[bits]
+    p, q, hs = k["p"], k["q"], k["hs"]
+    n = p * q
+    NL = int(bits) // 32
+    ms = [int(i["m"], 16) for i in items]
+    pt = batch_to_limbs(ms, NL)
+    r_djn = batch_to_limbs([int(i["r_djn"], 16) for i in items], NL // 2)
+    r_std = batch_to_limbs([int(i["r_std"], 16) for i in items], NL)
+    pk_djn = capi.PubKey(to_limbs(n, NL), to_limbs(hs, 2 * NL), int(bits) // 2)
+    pk_std = capi.PubKey(to_limbs(n, NL))
+    sk = capi.PrivKey(to_limbs(q, NL // 2), to_limbs(p, NL // 2))  # swapped on purpose
+    c_djn = pk_djn.encrypt(pt, r_djn)         # small batch: windowed hs^r
+    c_std = pk_std.encrypt(pt, r_std)
+    c_plain = pk_std.encrypt(pt, None, make_secure=False)
+    assert batch_from_limbs(c_djn) == [int(i["c_djn"], 16) for i in items]
+    assert batch_from_limbs(c_std) == [int(i["c_std"], 16) for i in items]
+    assert batch_from_limbs(c_plain) == [int(i["c_plain"], 16) for i in items]
+    assert batch_from_limbs(sk.decrypt(c_djn)) == ms
+    assert batch_from_limbs(sk.decrypt(c_std, use_crt=False)) == ms
+    nsq = to_limbs(n * n, 2 * NL)
+    assert batch_from_limbs(capi.modmul(c_djn, c_std, nsq)) == \
+        [int(i["c_add"], 16) for i in items]
+    kk = batch_to_limbs([int(i["k"], 16) for i in items], 2 * NL)
+    assert batch_from_limbs(capi.modexp(c_djn, kk, nsq, capi.SHARED_MOD)) == \
+        [int(i["c_mul"], 16) for i in items]
+
+
+@pytest.mark.parametrize("bits", ["1024", "2048", "3072"])
+def test_encrypt_decrypt_batch_vs_oracle(capi, oracle, keys, bits):
+    """larger batch: DJN through the fixed-base comb (count >= 64), non-DJN,
+    decrypt CRT and RAW, all against the oracle on the same seeded inputs"""
+    k = keys[bits]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL = int(bits) // 32
+    count = {"1024": 531, "2048": 203, "3072": 77}[bits]
+    rng = np.random.default_rng(int(bits))
+    pt = batch_to_limbs([int.from_bytes(rng.bytes(NL * 4), "little") % n
+                         for _ in range(count)], NL)
+    r_djn = random_limbs(rng, count, NL // 2)
+    r_std = batch_to_limbs([1 + int.from_bytes(rng.bytes(NL * 4), "little") % (n - 1)
+                            for _ in range(count)], NL)
+    nl = to_limbs(n, NL)
+    hsl = to_limbs(k["hs"], 2 * NL)
+    pk_djn = capi.PubKey(nl, hsl, int(bits) // 2)
+    pk_std = capi.PubKey(nl)
+    sk = capi.PrivKey(to_limbs(p, NL // 2), to_limbs(q, NL // 2))
+    c_djn = pk_djn.encrypt(pt, r_djn)
+    assert np.array_equal(c_djn, oracle.encrypt(nl, hsl, pt, r_djn))
+    c_std = pk_std.encrypt(pt[:40], r_std[:40])
+    assert np.array_equal(c_std, oracle.encrypt(nl, None, pt[:40], r_std[:40]))
+    d = sk.decrypt(c_djn)
+    assert np.array_equal(d, pt)
+    assert np.array_equal(d, oracle.decrypt_crt(to_limbs(p, NL // 2),
+                                                to_limbs(q, NL // 2), c_djn))
+    d_raw = sk.decrypt(c_djn[:40], use_crt=False)
+    assert np.array_equal(d_raw, pt[:40])
+    # wide injected randoms (the reference benchmark injects a 2047-bit r with
+    # DJN on, bench_cryptography.cpp:38-47,81-82): comb table is extended
+    r_wide = random_limbs(rng, 70, NL)
+    c_w = pk_djn.encrypt(pt[:70], r_wide)
+    assert np.array_equal(c_w, oracle.encrypt(nl, hsl, pt[:70], r_wide))
+
+
+def test_homomorphic_properties_large_batch(capi, keys):
+    """size-independent checks at a batch the oracle would need minutes for:
+    dec(enc(a) * enc(b)) = a + b mod n, dec(enc(a)^k) = a*k mod n."""
+    k = keys["2048"]
+    p, q = k["p"], k["q"]
+    n = p * q
+    NL = 64
+    count = 4096
+    rng = np.random.default_rng(2048)
+    a = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    b = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    r1 = random_limbs(rng, count, 32)
+    r2 = random_limbs(rng, count, 32)
+    kk = random_limbs(rng, count, 1)
+    pk = capi.PubKey(to_limbs(n, NL), to_limbs(k["hs"], 2 * NL), 1024)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    ca, cb = pk.encrypt(a, r1), pk.encrypt(b, r2)
+    nsq = to_limbs(n * n, 128)
+    s = sk.decrypt(capi.modmul(ca, cb, nsq))
+    m = sk.decrypt(capi.modexp(ca, kk, nsq, capi.SHARED_MOD))
+    A, B, S, M = (batch_from_limbs(x) for x in (a, b, s, m))
+    K = [int(x) for x in kk[:, 0]]
+    assert S == [(x + y) % n for x, y in zip(A, B)]
+    assert M == [(x * y) % n for x, y in zip(A, K)]
+    assert np.array_equal(sk.decrypt(ca), a)
+
+
+def test_int_peak_reports(capi):
+    macs, mhz = capi.int_peak()
+    assert macs > 1e12 and mhz > 500
