@@ -122,10 +122,13 @@ class PubKey:
         _check(lib().ipclb200_pubkey_create(_p(n), self.n_words, _p(hs_a),
                                             int(rand_bits), ctypes.byref(self._h)))
 
-    def encrypt(self, pt, r=None, make_secure=True):
+    def encrypt(self, pt, r=None, make_secure=True, out=None):
         pt = np.atleast_2d(_c(pt))
         r_a = None if r is None else np.atleast_2d(_c(r))
-        ct = np.zeros((pt.shape[0], 2 * self.n_words), dtype=np.uint32)
+        ct = out if out is not None else np.zeros(
+            (pt.shape[0], 2 * self.n_words), dtype=np.uint32)
+        assert ct.dtype == np.uint32 and ct.flags.c_contiguous
+        assert ct.shape == (pt.shape[0], 2 * self.n_words)
         _check(lib().ipclb200_encrypt(self._h, _p(pt), pt.shape[1], _p(r_a),
                                       0 if r_a is None else r_a.shape[1],
                                       ctypes.c_size_t(pt.shape[0]),
@@ -158,10 +161,13 @@ class PrivKey:
         _check(lib().ipclb200_privkey_create(_p(p), _p(q), self.p_words,
                                              ctypes.byref(self._h)))
 
-    def decrypt(self, ct, use_crt=True):
+    def decrypt(self, ct, use_crt=True, out=None):
         ct = np.atleast_2d(_c(ct))
         assert ct.shape[1] == 4 * self.p_words
-        pt = np.zeros((ct.shape[0], 2 * self.p_words), dtype=np.uint32)
+        pt = out if out is not None else np.zeros(
+            (ct.shape[0], 2 * self.p_words), dtype=np.uint32)
+        assert pt.dtype == np.uint32 and pt.flags.c_contiguous
+        assert pt.shape == (ct.shape[0], 2 * self.p_words)
         _check(lib().ipclb200_decrypt(self._h, _p(ct), ctypes.c_size_t(ct.shape[0]),
                                       int(use_crt), _p(pt)))
         return pt
