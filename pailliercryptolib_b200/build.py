@@ -101,10 +101,39 @@ def build_oracle(force=False):
     return ORACLE_LIB
 
 
+CPP_TEST_DIR = os.path.join(ROOT, "tests", "cpp")
+CPP_TEST_BIN = os.path.join(CPP_TEST_DIR, "_build", "ipcl_tests")
+BN_SHIM = os.path.join(CPP_TEST_DIR, "_build", "libbn_shim.so")
+
+
+def build_cpp_tests(force=False):
+    """tests/cpp/_build/ipcl_tests (the re-expressed reference gtests, needs a
+    GPU to run) and libbn_shim.so (host-only BigNumber checks)."""
+    build_ipcl()
+    inc = ["-I", os.path.join(PKG, "ipcl", "include"), "-I",
+           os.path.join(ROOT, "include"), "-I", CSRC]
+    os.makedirs(os.path.dirname(CPP_TEST_BIN), exist_ok=True)
+    srcs = [os.path.join(CPP_TEST_DIR, f) for f in
+            ("main.cpp", "test_cryptography.cpp", "test_ops.cpp")]
+    deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"), IPCL_LIB]
+    if force or not _newer(CPP_TEST_BIN, deps):
+        _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", CPP_TEST_BIN]
+             + srcs + ["-L", LIBDIR, "-lipcl", "-lipcl_b200",
+                       "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
+    shim_src = os.path.join(CPP_TEST_DIR, "bn_shim.cpp")
+    bn_src = os.path.join(PKG, "ipcl", "src", "bignum.cpp")
+    if force or not _newer(BN_SHIM, [shim_src, bn_src,
+                                     os.path.join(CSRC, "hostbn.hpp")]):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + inc +
+             ["-o", BN_SHIM, shim_src, bn_src])
+    return CPP_TEST_BIN
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_ipcl(force)
     build_oracle(force)
+    build_cpp_tests(force)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,54 @@
+// marshal.hpp -- vector<BigNumber> <-> flat little-endian limb buffers, the
+// data layout of the C ABI (include/ipcl_b200.h).  One pass, one memcpy per
+// element; replaces the per-chunk sub-vector copies and 8 x mod_dwords padding
+// buffers of ippMBModExp (ipcl/mod_exp.cpp:490-506,627-632).
+#ifndef IPCL_B200_SRC_MARSHAL_HPP_
+#define IPCL_B200_SRC_MARSHAL_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "ipcl/bignum.h"
+
+namespace ipcl {
+namespace detail {
+
+inline int maxWords(const std::vector<BigNumber>& v) {
+  std::size_t w = 1;
+  for (const auto& x : v)
+    if (x.words().size() > w) w = x.words().size();
+  return static_cast<int>(w);
+}
+
+// out: v.size() x words, zero padded.  Every element must be non-negative and
+// fit (callers reduce first).
+inline void pack(const std::vector<BigNumber>& v, int words,
+                 std::vector<uint32_t>& out) {
+  out.assign(v.size() * static_cast<std::size_t>(words), 0u);
+  for (std::size_t i = 0; i < v.size(); i++) {
+    const auto& w = v[i].words();
+    if (!w.empty())
+      std::memcpy(&out[i * static_cast<std::size_t>(words)], w.data(),
+                  w.size() * sizeof(uint32_t));
+  }
+}
+
+inline std::vector<BigNumber> unpack(const std::vector<uint32_t>& flat,
+                                     std::size_t count, int words) {
+  std::vector<BigNumber> r(count);
+  for (std::size_t i = 0; i < count; i++)
+    r[i].Set(&flat[i * static_cast<std::size_t>(words)], words, IppsBigNumPOS);
+  return r;
+}
+
+inline bool allEqual(const std::vector<BigNumber>& v) {
+  for (std::size_t i = 1; i < v.size(); i++)
+    if (v[i].words() != v[0].words() || v[i].isNegative() != v[0].isNegative())
+      return false;
+  return true;
+}
+
+}  // namespace detail
+}  // namespace ipcl
+#endif  // IPCL_B200_SRC_MARSHAL_HPP_

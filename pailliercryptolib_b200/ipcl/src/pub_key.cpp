@@ -1,0 +1,204 @@
+// pub_key.cpp -- ipcl::PublicKey on the B200 back-end.
+//
+// Reference: ipcl/pub_key.cpp.  There encrypt() is a serial host loop
+// ct = (n*pt + 1) % n^2 (:105), one modExp batch for the obfuscator (:63 DJN
+// hs^r, :79 r^n) and a second serial host loop of mul + mod (:88-89).  Here all
+// three stages are one fused kernel behind ipclb200_encrypt; the host only
+// marshals plaintexts and randoms.
+#include "ipcl/pub_key.hpp"
+
+#include <mutex>
+
+#include "ipcl/ciphertext.hpp"
+#include "ipcl/mod_exp.hpp"
+#include "ipcl/utils/util.hpp"
+#include "ipcl_b200.h"
+#include "marshal.hpp"
+
+namespace ipcl {
+
+struct PublicKey::DeviceKey {
+  ipclb200_pubkey* h = nullptr;
+  ~DeviceKey() {
+    if (h) ipclb200_pubkey_destroy(h);
+  }
+};
+
+static std::mutex g_pk_mutex;  // guards lazy creation; encrypt() is const and
+                               // is called concurrently on one key
+                               // (test/test_cryptography.cpp:45-57)
+
+PublicKey::PublicKey(const BigNumber& n, int bits, bool enableDJN_)
+    : m_n(std::make_shared<BigNumber>(n)),
+      m_g(std::make_shared<BigNumber>(*m_n + 1)),
+      m_nsquare(std::make_shared<BigNumber>((*m_n) * (*m_n))),
+      m_bits(bits),
+      m_dwords(BITSIZE_DWORD(bits * 2)),
+      m_hs(0u),
+      m_randbits(0),
+      m_enable_DJN(false),
+      m_testv(false) {
+  if (enableDJN_) this->enableDJN();
+  m_isInitialized = true;
+}
+
+// hs = (-x^2)^n mod n^2 for a random x coprime to n (pub_key.cpp:32-49)
+void PublicKey::enableDJN() {
+  BigNumber rmod;
+  for (;;) {
+    BigNumber rand = getRandomBN(m_n->BitSize() + 128);
+    rmod = rand % (*m_n);
+    if (rand.gcd(*m_n) == BigNumber::One()) break;
+  }
+  BigNumber h = (rmod * rmod * BigNumber(static_cast<Ipp32s>(-1))) % (*m_n);
+  m_hs = modExp(h, *m_n, *m_nsquare);
+  m_randbits = m_bits >> 1;
+  m_enable_DJN = true;
+  resetDeviceKey();
+}
+
+void PublicKey::setDJN(const BigNumber& hs, int randbit) {
+  if (m_enable_DJN) return;
+  m_hs = hs;
+  m_randbits = randbit;
+  m_enable_DJN = true;
+  resetDeviceKey();
+}
+
+void PublicKey::setRandom(const std::vector<BigNumber>& r) {
+  m_r.insert(m_r.end(), r.begin(), r.end());
+  m_testv = true;
+}
+
+void PublicKey::setHS(const BigNumber& hs) {
+  m_hs = hs;
+  resetDeviceKey();
+}
+
+void PublicKey::create(const BigNumber& n, int bits, bool enableDJN_) {
+  m_n = std::make_shared<BigNumber>(n);
+  m_g = std::make_shared<BigNumber>(*m_n + 1);
+  m_nsquare = std::make_shared<BigNumber>((*m_n) * (*m_n));
+  m_bits = bits;
+  m_dwords = BITSIZE_DWORD(bits * 2);
+  m_enable_DJN = false;
+  m_hs = BigNumber::Zero();
+  m_randbits = 0;
+  m_r.clear();
+  m_testv = false;
+  resetDeviceKey();
+  if (enableDJN_) this->enableDJN();
+  m_isInitialized = true;
+}
+
+void PublicKey::create(const BigNumber& n, int bits, const BigNumber& hs,
+                       int randbits) {
+  create(n, bits, false);
+  m_enable_DJN = true;
+  m_hs = hs;
+  m_randbits = randbits;
+  resetDeviceKey();
+}
+
+ipclb200_pubkey* PublicKey::deviceKey() const {
+  std::lock_guard<std::mutex> lk(g_pk_mutex);
+  if (!m_dev) {
+    auto dk = std::make_shared<DeviceKey>();
+    const int nl = static_cast<int>(m_n->words().size());
+    std::vector<uint32_t> n_w(static_cast<std::size_t>(nl));
+    m_n->toWords(n_w.data(), n_w.size());
+    std::vector<uint32_t> hs_w;
+    if (m_enable_DJN) {
+      BigNumber hs = m_hs % (*m_nsquare);
+      hs_w.resize(2 * static_cast<std::size_t>(nl));
+      hs.toWords(hs_w.data(), hs_w.size());
+    }
+    DEVICE_CHECK(ipclb200_pubkey_create(n_w.data(), nl,
+                                        m_enable_DJN ? hs_w.data() : nullptr,
+                                        m_randbits, &dk->h));
+    m_dev = dk;
+  }
+  return m_dev->h;
+}
+
+std::vector<BigNumber> PublicKey::drawRandoms(std::size_t sz) const {
+  std::vector<BigNumber> r;
+  if (m_testv) {
+    ERROR_CHECK(m_r.size() >= sz,
+                "encrypt: fewer injected randoms (setRandom) than plaintexts");
+    r.assign(m_r.begin(), m_r.begin() + static_cast<std::ptrdiff_t>(sz));
+    return r;
+  }
+  r.resize(sz);
+  if (m_enable_DJN) {
+    for (auto& x : r) x = getRandomBN(m_randbits);  // pub_key.cpp:59-61
+  } else {
+    const BigNumber nm1 = *m_n - 1;
+    for (auto& x : r) x = getRandomBN(m_bits) % nm1 + 1;  // pub_key.cpp:74-77
+  }
+  return r;
+}
+
+std::vector<BigNumber> PublicKey::getDJNObfuscator(std::size_t sz) const {
+  std::vector<BigNumber> base(sz, m_hs);
+  std::vector<BigNumber> sq(sz, *m_nsquare);
+  return modExp(base, drawRandoms(sz), sq);
+}
+
+std::vector<BigNumber> PublicKey::getNormalObfuscator(std::size_t sz) const {
+  std::vector<BigNumber> sq(sz, *m_nsquare);
+  std::vector<BigNumber> pown(sz, *m_n);
+  return modExp(drawRandoms(sz), pown, sq);
+}
+
+void PublicKey::applyObfuscator(std::vector<BigNumber>& ciphertext) const {
+  const std::size_t sz = ciphertext.size();
+  if (sz == 0) return;
+  std::vector<BigNumber> obf =
+      m_enable_DJN ? getDJNObfuscator(sz) : getNormalObfuscator(sz);
+  ciphertext = modMul(ciphertext, obf, *m_nsquare);
+}
+
+std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
+                                              bool make_secure) const {
+  const std::size_t sz = pt.size();
+  const int nl = static_cast<int>(m_n->words().size());
+  ipclb200_pubkey* dev = deviceKey();
+
+  // (n*pt + 1) mod n^2 only depends on pt mod n; bring negative or oversize
+  // plaintexts into [0, n) so they fit the n-word slot
+  const std::vector<BigNumber>* pp = &pt;
+  std::vector<BigNumber> reduced;
+  for (std::size_t i = 0; i < sz; i++) {
+    if (pt[i].isNegative() || static_cast<int>(pt[i].words().size()) > nl) {
+      if (reduced.empty()) reduced = pt;
+      reduced[i] = pt[i] % (*m_n);
+      pp = &reduced;
+    }
+  }
+  std::vector<uint32_t> f_pt, f_r, f_ct(sz * 2 * static_cast<std::size_t>(nl));
+  detail::pack(*pp, nl, f_pt);
+  int r_words = 0;
+  if (make_secure) {
+    std::vector<BigNumber> r = drawRandoms(sz);
+    for (auto& x : r) {
+      ERROR_CHECK(!x.isNegative(), "encrypt: negative random");
+      if (static_cast<int>(x.words().size()) > 2 * nl) x = x % (*m_nsquare);
+    }
+    r_words = detail::maxWords(r);
+    detail::pack(r, r_words, f_r);
+  }
+  DEVICE_CHECK(ipclb200_encrypt(dev, f_pt.data(), nl,
+                                make_secure ? f_r.data() : nullptr, r_words, sz,
+                                make_secure ? 1 : 0, f_ct.data()));
+  return detail::unpack(f_ct, sz, 2 * nl);
+}
+
+CipherText PublicKey::encrypt(const PlainText& pt, bool make_secure) const {
+  ERROR_CHECK(m_isInitialized, "encrypt: Public key is NOT initialized.");
+  const std::size_t pt_size = pt.getSize();
+  ERROR_CHECK(pt_size > 0, "encrypt: Cannot encrypt empty PlainText");
+  return CipherText(*this, raw_encrypt(pt.texts(), make_secure));
+}
+
+}  // namespace ipcl
