@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-sample", type=int, default=2048,
+    ap.add_argument("--cpu-sample", type=int, default=4096,
                     help="elements of the workload timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -303,13 +303,26 @@ def main():
     sampler.join(timeout=2)
     assert np.array_equal(dt_pin.numpy().view(np.uint32), pt_h), "e2e round trip failed"
 
+    from pailliercryptolib_b200 import sharding
+    # the scatter/gather a single-owner batch would need (north_star: "NCCL
+    # only for the trivial scatter/gather"); outside the timed region
+    sg_ms = None
     if world > 1:
-        t = torch.tensor([step_ms, e2e_ms, float(np.mean(enc_ms)),
-                          float(np.mean(dec_ms))], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_ms, enc_mean, dec_mean = [float(x) for x in t.tolist()]
-    else:
-        enc_mean, dec_mean = float(np.mean(enc_ms)), float(np.mean(dec_ms))
+        full = d_pt.repeat(world, 1) if rank == 0 else None
+        for _ in range(2):
+            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+            barrier()
+            e0.record()
+            loc = sharding.scatter_rows(full, B * world, NL, torch.int32, dev)
+            back = sharding.gather_rows(loc, B * world)
+            e1.record()
+            e1.synchronize()
+            sg_ms = e0.elapsed_time(e1)
+        del full, loc, back
+    step_ms, e2e_ms, enc_mean, dec_mean = sharding.max_over_ranks(
+        [step_ms, e2e_ms, float(np.mean(enc_ms)), float(np.mean(dec_ms))], dev)
+    if sg_ms is not None:
+        sg_ms = sharding.max_over_ranks([sg_ms], dev)[0]
 
     if rank == 0:
         total = B * world
@@ -379,6 +392,8 @@ def main():
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
+        if sg_ms is not None:
+            line["nccl_scatter_gather_ms"] = sg_ms
         if not args.no_cpu_baseline and world == 1:
             res = cpu_reference(args.cpu_sample)
             line["cpu_baseline"] = {

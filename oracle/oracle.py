@@ -97,3 +97,45 @@ def decrypt_raw(n, lam, x, ct):
     if rc:
         raise ValueError("orc_decrypt_raw rc=%d" % rc)
     return pt
+
+
+# ---- 8-lane AVX512-IFMA restatement of mbx_exp_mb8 (ifma_modexp.c) ----------
+def have_ifma():
+    L = lib()
+    return bool(L.orc_have_ifma())
+
+
+def modexp_mb8(base, exp, mod, shared_base=False, shared_exp=False):
+    """shared modulus only (the shape of every call on the Paillier path)"""
+    base, exp, mod = _c(base), _c(exp), _c(mod)
+    L, EL = mod.shape[-1], exp.shape[-1]
+    count = max(np.atleast_2d(base).shape[0], np.atleast_2d(exp).shape[0])
+    out = np.zeros((count, L), dtype=np.uint32)
+    rc = lib().orc_modexp_mb8(_p(base), ctypes.c_size_t(0 if shared_base else L),
+                              _p(exp), ctypes.c_size_t(0 if shared_exp else EL),
+                              EL, _p(mod), L, ctypes.c_size_t(count), _p(out))
+    if rc:
+        raise ValueError("orc_modexp_mb8 rc=%d" % rc)
+    return out
+
+
+def encrypt_mb8(n, hs, pt, r):
+    n, hs, pt, r = _c(n), _c(hs), _c(pt), _c(r)
+    NL = n.shape[-1]
+    ct = np.zeros((pt.shape[0], 2 * NL), dtype=np.uint32)
+    rc = lib().orc_encrypt_mb8(_p(n), NL, _p(hs), _p(pt), _p(r), r.shape[-1],
+                               ctypes.c_size_t(pt.shape[0]), _p(ct))
+    if rc:
+        raise ValueError("orc_encrypt_mb8 rc=%d" % rc)
+    return ct
+
+
+def decrypt_crt_mb8(p, q, ct):
+    p, q, ct = _c(p), _c(q), _c(ct)
+    PL = p.shape[-1]
+    pt = np.zeros((ct.shape[0], 2 * PL), dtype=np.uint32)
+    rc = lib().orc_decrypt_crt_mb8(_p(p), _p(q), PL, _p(ct),
+                                   ctypes.c_size_t(ct.shape[0]), _p(pt))
+    if rc:
+        raise ValueError("orc_decrypt_crt_mb8 rc=%d" % rc)
+    return pt

@@ -489,3 +489,131 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ */
+/* multi-buffer (8-lane AVX512-IFMA) variants: same functions, with the */
+/* modexp stage going through ifma_modexp.c the way the reference goes  */
+/* through mbx_exp_mb8.  Used as the CPU baseline when the host has IFMA.*/
+/* ------------------------------------------------------------------ */
+int orc_have_ifma(void);
+int orc_modexp_mb8(const u32* base, size_t base_stride, const u32* exp,
+                   size_t exp_stride, int EL, const u32* mod, int L,
+                   size_t count, u32* out);
+
+/* R = 2^(52 len): RR = R^2 mod m as 52-bit digits, k0 = -m^-1 mod 2^52 */
+int orc_radix52_constants(const u32* mod, int L, int len, u64* rr52, u64* k0) {
+  int bits = 2 * 52 * len;
+  int tw = bits / 32 + 1;
+  if (tw > 2 * ORC_MAX_WORDS + 1 || L > ORC_MAX_WORDS) return -2;
+  u32* t = calloc((size_t)tw, sizeof(u32));
+  u32 r[ORC_MAX_WORDS];
+  t[bits >> 5] = 1u << (bits & 31);
+  bn_mod(r, t, tw, mod, L);
+  free(t);
+  for (int j = 0; j < len; j++) {
+    u64 v = 0;
+    for (int k = 0; k < 52; k++) {
+      int b = j * 52 + k;
+      if ((b >> 5) < L) v |= (u64)((r[b >> 5] >> (b & 31)) & 1u) << k;
+    }
+    rr52[j] = v;
+  }
+  u64 n0 = mod[0] | (L > 1 ? (u64)mod[1] << 32 : 0);
+  u64 x = n0;
+  for (int i = 0; i < 6; i++) x *= 2 - n0 * x;
+  *k0 = (0 - x) & ((1ull << 52) - 1);
+  return 0;
+}
+
+int orc_encrypt_mb8(const u32* n, int NL, const u32* hs, const u32* pt,
+                    const u32* r, int RL, size_t count, u32* ct) {
+  int L = 2 * NL;
+  if (NL <= 0 || L > ORC_MAX_WORDS || RL > L) return -2;
+  u32 nsq[ORC_MAX_WORDS];
+  bn_mul(nsq, n, NL, n, NL);
+  u32* gm = malloc(sizeof(u32) * count * (size_t)L);
+  u32* obf = malloc(sizeof(u32) * count * (size_t)L);
+  /* the reference runs this loop serially (pub_key.cpp:105); OpenMP here only
+   * flatters the baseline */
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < count; i++) {
+    u32 t[2 * ORC_MAX_WORDS + 1];
+    bn_mul(t, n, NL, pt + i * (size_t)NL, NL);
+    u64 cy = 1;
+    for (int j = 0; j < L && cy; j++) {
+      cy += t[j];
+      t[j] = (u32)cy;
+      cy >>= 32;
+    }
+    t[L] = (u32)cy;
+    bn_mod(gm + i * (size_t)L, t, L + 1, nsq, L);
+  }
+  int rc;
+  if (hs) {
+    rc = orc_modexp_mb8(hs, 0, r, (size_t)RL, RL, nsq, L, count, obf);
+  } else {
+    u32* rb = calloc(count * (size_t)L, sizeof(u32));
+    for (size_t i = 0; i < count; i++)
+      memcpy(rb + i * (size_t)L, r + i * (size_t)RL, sizeof(u32) * (size_t)RL);
+    rc = orc_modexp_mb8(rb, (size_t)L, n, 0, NL, nsq, L, count, obf);
+    free(rb);
+  }
+  if (!rc) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < count; i++)
+      bn_modmul(ct + i * (size_t)L, gm + i * (size_t)L, obf + i * (size_t)L, nsq, L);
+  }
+  free(gm);
+  free(obf);
+  return rc;
+}
+
+int orc_decrypt_crt_mb8(const u32* p, const u32* q, int PL, const u32* ct,
+                        size_t count, u32* pt) {
+  int NL = 2 * PL, CL = 2 * NL;
+  if (PL <= 0 || CL > ORC_MAX_WORDS) return -2;
+  u32 psq[ORC_MAX_WORDS], qsq[ORC_MAX_WORDS], hp[ORC_MAX_WORDS];
+  u32 hq[ORC_MAX_WORDS], pinv[ORC_MAX_WORDS], pm1[ORC_MAX_WORDS];
+  u32 qm1[ORC_MAX_WORDS];
+  int rc = orc_crt_constants(p, q, PL, psq, qsq, hp, hq, pinv);
+  if (rc) return rc;
+  bn_sub_word(pm1, p, 1, PL);
+  bn_sub_word(qm1, q, 1, PL);
+  u32* bp = malloc(sizeof(u32) * count * (size_t)NL);
+  u32* bq = malloc(sizeof(u32) * count * (size_t)NL);
+  u32* rp = malloc(sizeof(u32) * count * (size_t)NL);
+  u32* rq = malloc(sizeof(u32) * count * (size_t)NL);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < count; i++) { /* pri_key.cpp:127-130 */
+    bn_mod(bp + i * (size_t)NL, ct + i * (size_t)CL, CL, psq, NL);
+    bn_mod(bq + i * (size_t)NL, ct + i * (size_t)CL, CL, qsq, NL);
+  }
+  rc = orc_modexp_mb8(bp, (size_t)NL, pm1, 0, PL, psq, NL, count, rp); /* :133 */
+  if (!rc) rc = orc_modexp_mb8(bq, (size_t)NL, qm1, 0, PL, qsq, NL, count, rq);
+  if (!rc) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < count; i++) { /* :141-145 */
+      u32 lp[ORC_MAX_WORDS], lq[ORC_MAX_WORDS], dp[ORC_MAX_WORDS];
+      u32 dq[ORC_MAX_WORDS], u[ORC_MAX_WORDS], dpq[ORC_MAX_WORDS];
+      u32 diff[ORC_MAX_WORDS], t[2 * ORC_MAX_WORDS];
+      l_fun(lp, PL, rp + i * (size_t)NL, NL, p, PL);
+      l_fun(lq, PL, rq + i * (size_t)NL, NL, q, PL);
+      bn_modmul(dp, lp, hp, p, PL);
+      bn_modmul(dq, lq, hq, q, PL);
+      bn_mod(dpq, dp, PL, q, PL);
+      int neg = bn_cmp(dq, dpq, PL) < 0;
+      bn_sub(diff, dq, dpq, PL);
+      if (neg) bn_add(diff, diff, q, PL);
+      bn_modmul(u, diff, pinv, q, PL);
+      bn_mul(t, u, PL, p, PL);
+      memset(lp, 0, sizeof(u32) * (size_t)NL);
+      memcpy(lp, dp, sizeof(u32) * (size_t)PL);
+      bn_add(pt + i * (size_t)NL, t, lp, NL);
+    }
+  }
+  free(bp);
+  free(bq);
+  free(rp);
+  free(rq);
+  return rc;
+}

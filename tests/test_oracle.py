@@ -101,3 +101,41 @@ def test_scheme_golden(oracle, keys, scheme_vectors):
         kk = batch_to_limbs([int(i["k"], 16) for i in items], 2 * NL)
         mul = oracle.modexp(c_djn, kk, nsq[None, :], shared_mod=True)
         assert batch_from_limbs(mul) == [int(i["c_mul"], 16) for i in items]
+
+
+def test_mb8_matches_scalar(oracle, iso, keys):
+    """the AVX512-IFMA multi-buffer restatement (CPU baseline) is bit-exact
+    with the scalar oracle and reproduces the ISO known answers"""
+    import pytest
+    if not oracle.have_ifma():
+        pytest.skip("host has no AVX512-IFMA")
+    rng = np.random.default_rng(5)
+    from pailliercryptolib_b200.limbs import random_limbs
+    for L, EL, count in [(32, 16, 19), (64, 32, 21), (96, 8, 9), (128, 32, 13)]:
+        mod = random_limbs(rng, 1, L)
+        mod[0, 0] |= 1
+        mod[0, -1] |= 0x80000000
+        base = random_limbs(rng, count, L)
+        base[0] = 0
+        base[1] = 0
+        base[1, 0] = 1
+        exp = random_limbs(rng, count, EL)
+        exp[2] = 0
+        want = oracle.modexp(base, exp, mod, shared_mod=True)
+        got = oracle.modexp_mb8(base, exp, mod[0])
+        assert np.array_equal(got, want), L
+    n = iso["p"] * iso["q"]
+    ms = [iso["m0"], iso["m1"]] + [iso["m0"]] * 7
+    rs = [iso["r0"], iso["r1"]] + [iso["r0"]] * 7
+    ct = oracle.encrypt_mb8(to_limbs(n, 64), None, batch_to_limbs(ms, 64),
+                            batch_to_limbs(rs, 64))
+    assert from_limbs(ct[0]) == iso["c1"] and from_limbs(ct[1]) == iso["c2"]
+    p, q = sorted((iso["p"], iso["q"]))
+    d = oracle.decrypt_crt_mb8(to_limbs(p, 32), to_limbs(q, 32), ct)
+    assert batch_from_limbs(d) == ms
+    k = keys["2048"]
+    hs = to_limbs(k["hs"], 128)
+    pt = random_limbs(rng, 11, 64, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, 11, 32)
+    assert np.array_equal(oracle.encrypt_mb8(to_limbs(n, 64), hs, pt, r),
+                          oracle.encrypt(to_limbs(n, 64), hs, pt, r))
