@@ -24,11 +24,17 @@ def shard_sizes(count, world):
             for r in range(world)]
 
 
+def _world_rank(group):
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
 def scatter_rows(full, count, cols, dtype, device, src=0, group=None):
     """Rank `src` holds `full` (count x cols); every rank gets its block.
     Grouped point-to-point sends: NCCL has no native scatter with ragged
     sizes, batched isend/irecv is the idiom."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = _world_rank(group)
     s, e = shard_range(count, world, rank)
     local = torch.empty((e - s, cols), dtype=dtype, device=device)
     if world == 1:
@@ -53,7 +59,7 @@ def scatter_rows(full, count, cols, dtype, device, src=0, group=None):
 def gather_rows(local, count, dst=0, group=None):
     """Inverse of scatter_rows: rank `dst` returns the (count x cols) result,
     the others return None."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = _world_rank(group)
     if world == 1:
         return local
     cols = local.shape[1]
