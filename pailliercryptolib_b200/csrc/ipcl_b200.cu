@@ -93,6 +93,40 @@ int pick_window(int ebits) {
   return best;
 }
 
+constexpr int kSchedWindow = 5;  // 16 odd powers per table
+
+// left-to-right sliding-window schedule for a fixed exponent (format: see
+// modexp_sched_core in kernels.cuh).  e > 0.
+std::vector<uint8_t> build_schedule(const Limbs& e, int w) {
+  std::vector<uint8_t> s;
+  s.push_back((uint8_t)(1 << (w - 1)));
+  auto bit = [&](int i) { return i >= 0 && ((e[(size_t)i / 32] >> (i % 32)) & 1u); };
+  int i = hbn::bitlen(e) - 1;
+  bool first = true;
+  while (i >= 0) {
+    if (!bit(i)) {
+      s.push_back(0);
+      i--;
+      continue;
+    }
+    int l = i - w + 1;
+    if (l < 0) l = 0;
+    while (!bit(l)) l++;
+    unsigned v = 0;
+    for (int k = i; k >= l; k--) v = (v << 1) | (bit(k) ? 1u : 0u);
+    if (first) {
+      s.push_back((uint8_t)((v - 1) / 2));
+      first = false;
+    } else {
+      for (int k = i; k >= l; k--) s.push_back(0);
+      s.push_back((uint8_t)((v - 1) / 2 + 1));
+    }
+    i = l - 1;
+  }
+  s.push_back(0xff);
+  return s;
+}
+
 // ---------------------------------------------------------------------------
 // per-modulus constants
 // ---------------------------------------------------------------------------
@@ -265,8 +299,12 @@ int grid_for(Kern kern, size_t groups, int T, int* grid) {
   size_t gpb = kBlockThreads / T;
   size_t need = (groups + gpb - 1) / gpb;
   size_t cap = (size_t)per_sm * g_ctx.sms;
-  *grid = (int)(need < cap ? need : cap);
-  if (*grid < 1) *grid = 1;
+  if (need < 1) need = 1;
+  // every group runs the same number of iterations; size the grid so the last
+  // iteration is not mostly padding (e.g. 4096 blocks of work on 592 resident:
+  // 7 iterations of 586 blocks instead of 7 of 592)
+  size_t iters = (need + cap - 1) / cap;
+  *grid = (int)((need + iters - 1) / iters);
   return 0;
 }
 
@@ -383,8 +421,12 @@ struct ipclb200_privkey {
   uint32_t p_inv32 = 0, q_inv32 = 0, p_n0inv = 0, q_n0inv = 0, n_inv32 = 0,
            n_n0inv = 0;
   int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
+  // sliding-window schedules of the shared exponents p-1, q-1
+  uint8_t* d_sched = nullptr;
+  const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr;
   ~ipclb200_privkey() {
     if (d_const) cudaFree(d_const);
+    if (d_sched) cudaFree(d_sched);
   }
 };
 
@@ -489,14 +531,25 @@ int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
 
 int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
   const int L = pk->L;
-  const int w = 8;
+  if (pk->d_comb && pk->comb_windows * pk->comb_w >= bits) return 0;
+  // widest window (<= 11 bits) whose table stays under 160 MB: 1024-bit r at
+  // a 2048-bit key -> w = 11, 94 windows x 2048 entries x 512 B = 98 MB
+  // (measured on B200: w = 8/9/10/11 -> 40.4/36.0/32.6/30.1 ms per 65536)
+  int w = 11;
+  while (w > 4 && (size_t)((bits + w - 1) / w) * ((size_t)L << w) * 4 > (160u << 20)) w--;
+  if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
+    int v = atoi(cw);
+    if (v >= 1 && v <= 12) w = v;
+  }
   int windows = (bits + w - 1) / w;
   if (windows < 1) windows = 1;
-  if (pk->d_comb && pk->comb_windows >= windows) return 0;
   if (pk->d_comb) {
+    // a wider exponent than the table covers: rebuild with the width the new
+    // size allows (keeps comb_w consistent with the table in memory)
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaFree(pk->d_comb));
     pk->d_comb = nullptr;
+    pk->comb_windows = 0;
   }
   size_t words = (size_t)windows * ((size_t)L << w);
   CUDA_TRY(cudaMalloc(&pk->d_comb, words * sizeof(uint32_t)));
@@ -589,20 +642,17 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     p.ct = d_ct;
     p.m[0] = sk->mp2->mc;
     p.m[1] = sk->mq2->mc;
-    p.e[0] = sk->d_pm1;
-    p.e[1] = sk->d_qm1;
-    p.e_words = pl;
-    p.e_bits[0] = sk->pm1_bits;
-    p.e_bits[1] = sk->qm1_bits;
+    p.sched[0] = sk->d_sched_p;
+    p.sched[1] = sk->d_sched_q;
     p.x = d_x;
     p.count = count;
-    p.window = pick_window(sk->qm1_bits);
+    p.table_entries = 1 << (kSchedWindow - 1);
     int grid = 0;
 #define F(K_, T_)                                                          \
   {                                                                        \
     TRY(grid_for(decrypt_crt_kernel<K_, T_>, 2 * count, T_, &grid));       \
     size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
-    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),           \
+    TRY(table_ws_get((void*)s, groups * ((size_t)L * p.table_entries),     \
                      &p.table_ws));                                        \
     decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
   }
@@ -1018,6 +1068,16 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   sk->n_inv32 = 0u - sk->n_n0inv;
   sk->pm1_bits = hbn::bitlen(pm1);
   sk->qm1_bits = hbn::bitlen(qm1);
+  {
+    std::vector<uint8_t> sp = build_schedule(pm1, kSchedWindow);
+    std::vector<uint8_t> sq = build_schedule(qm1, kSchedWindow);
+    std::vector<uint8_t> both(sp);
+    both.insert(both.end(), sq.begin(), sq.end());
+    CUDA_TRY(cudaMalloc(&sk->d_sched, both.size()));
+    CUDA_TRY(cudaMemcpy(sk->d_sched, both.data(), both.size(), cudaMemcpyHostToDevice));
+    sk->d_sched_p = sk->d_sched;
+    sk->d_sched_q = sk->d_sched + sp.size();
+  }
   sk->lambda_bits = hbn::bitlen(lam);
   *out = sk.release();
   return 0;
