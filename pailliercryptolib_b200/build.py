@@ -114,7 +114,8 @@ def build_cpp_tests(force=False):
            os.path.join(ROOT, "include"), "-I", CSRC]
     os.makedirs(os.path.dirname(CPP_TEST_BIN), exist_ok=True)
     srcs = [os.path.join(CPP_TEST_DIR, f) for f in
-            ("main.cpp", "test_cryptography.cpp", "test_ops.cpp")]
+            ("main.cpp", "test_cryptography.cpp", "test_ops.cpp",
+             "test_serialization.cpp")]
     deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"), IPCL_LIB]
     if force or not _newer(CPP_TEST_BIN, deps):
         _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", CPP_TEST_BIN]

@@ -95,6 +95,29 @@ int pick_window(int ebits) {
 
 constexpr int kSchedWindow = 5;  // 16 odd powers per table
 
+// byte code for decrypt_tile_kernel (opcodes: kernels.cuh) from a
+// sliding-window schedule: reduce the ciphertext, enter Montgomery form, build
+// the odd powers x, x^3, ... with x^2 parked in an extra slot, run the
+// schedule, leave Montgomery form
+std::vector<uint8_t> build_tile_program(const std::vector<uint8_t>& sched) {
+  const int nodd = sched[0];
+  std::vector<uint8_t> p = {0xc0, 0xc1, 0x40};
+  if (nodd > 1) {
+    p.push_back(0x00);
+    p.push_back((uint8_t)(0x40 + nodd));
+    p.push_back(0x80);
+    for (int k = 1; k < nodd; k++) {
+      p.push_back((uint8_t)(0x01 + nodd));
+      p.push_back((uint8_t)(0x40 + k));
+    }
+  }
+  p.push_back((uint8_t)(0x80 + sched[1]));
+  for (size_t i = 2; sched[i] != 0xff; i++)
+    p.push_back(sched[i] == 0 ? 0x00 : sched[i]);  // multiply by slot op-1
+  p.push_back(0xc2);
+  return p;
+}
+
 // left-to-right sliding-window schedule for a fixed exponent (format: see
 // modexp_sched_core in kernels.cuh).  e > 0.
 std::vector<uint8_t> build_schedule(const Limbs& e, int w) {
@@ -424,6 +447,10 @@ struct ipclb200_privkey {
   // sliding-window schedules of the shared exponents p-1, q-1
   uint8_t* d_sched = nullptr;
   const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr;
+  // byte-code programs of the thread-per-integer kernel and -N^-1 mod 2^256
+  const uint8_t *d_prog_p = nullptr, *d_prog_q = nullptr;
+  uint32_t ninv_p[8] = {}, ninv_q[8] = {};
+  int tile_slots = 0;
   ~ipclb200_privkey() {
     if (d_const) cudaFree(d_const);
     if (d_sched) cudaFree(d_sched);
@@ -636,7 +663,71 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
                      uint32_t* d_x /* count x 4*pl words scratch */,
                      cudaStream_t s) {
   const int pl = sk->pl;
-  if (use_crt) {
+  // the thread-per-integer kernel (mont_tile.cuh) does 15 % fewer multiplies
+  // but measured slower on B200 (194 ms vs 165 ms per 65536 at a 2048-bit
+  // key: only 8 warps/SM fit its shared-memory columns and it issues 2.7
+  // instructions per multiply); it stays opt-in
+  const char* force = getenv("IPCLB200_DECRYPT");
+  const bool tile = force && !strcmp(force, "tile");
+  if (use_crt && tile && (sk->L == 32 || sk->L == 48 || sk->L == 64)) {
+    const int L = sk->L;
+    DecryptTileParams p{};
+    p.ct = d_ct;
+    p.m0 = sk->mp2->mc;
+    p.m1 = sk->mq2->mc;
+    p.ninv0_lo = make_uint4(sk->ninv_p[0], sk->ninv_p[1], sk->ninv_p[2], sk->ninv_p[3]);
+    p.ninv0_hi = make_uint4(sk->ninv_p[4], sk->ninv_p[5], sk->ninv_p[6], sk->ninv_p[7]);
+    p.ninv1_lo = make_uint4(sk->ninv_q[0], sk->ninv_q[1], sk->ninv_q[2], sk->ninv_q[3]);
+    p.ninv1_hi = make_uint4(sk->ninv_q[4], sk->ninv_q[5], sk->ninv_q[6], sk->ninv_q[7]);
+    p.prog0 = sk->d_prog_p;
+    p.prog1 = sk->d_prog_q;
+    p.x = d_x;
+    p.count = count;
+    p.slots = sk->tile_slots;
+    constexpr int NT = 128;
+    const int V = L / 4;
+    const size_t smem = (size_t)(3 * V * NT + 4 * V) * 16;
+    int grid = 0;
+#define FT(NB_)                                                                   \
+  {                                                                               \
+    auto kern = decrypt_tile_kernel<NB_, NT>;                                     \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                    \
+    int per_sm = 0;                                                               \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem)); \
+    if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "tile kernel does not fit an SM"); \
+    size_t need = (2 * ((count + 31) / 32) + NT / 32 - 1) / (NT / 32);            \
+    size_t cap = (size_t)per_sm * g_ctx.sms;                                      \
+    grid = (int)(need < cap ? need : cap);                                        \
+    size_t ws_words = (size_t)grid * (NT / 32) * p.slots * V * 32 * 4 + 4;        \
+    uint32_t* ws = nullptr;                                                       \
+    TRY(table_ws_get((void*)s, ws_words, &ws));                                   \
+    p.table_ws = reinterpret_cast<uint4*>(ws);                                    \
+    p.work_counter = ws + (ws_words - 4);                                         \
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, 16, s));                          \
+    kern<<<grid, NT, smem, s>>>(p);                                               \
+  }
+    if (L == 32) FT(4) else if (L == 48) FT(6) else FT(8)
+#undef FT
+    CrtFinishParams f{};
+    f.x = d_x;
+    f.p = sk->d_p;
+    f.q = sk->d_q;
+    f.hpR = sk->d_hpR;
+    f.hqR = sk->d_hqR;
+    f.pinvR = sk->d_pinvR;
+    f.p_inv32 = sk->p_inv32;
+    f.q_inv32 = sk->q_inv32;
+    f.p_n0inv = sk->p_n0inv;
+    f.q_n0inv = sk->q_n0inv;
+    f.pl = pl;
+    f.xl = L;
+    f.pt = d_pt;
+    f.count = count;
+    crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
+    g_ctx.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  } else if (use_crt) {
     const int L = sk->L;
     DecryptCrtParams p{};
     p.ct = d_ct;
@@ -1071,12 +1162,23 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   {
     std::vector<uint8_t> sp = build_schedule(pm1, kSchedWindow);
     std::vector<uint8_t> sq = build_schedule(qm1, kSchedWindow);
+    std::vector<uint8_t> pp = build_tile_program(sp), pq = build_tile_program(sq);
     std::vector<uint8_t> both(sp);
     both.insert(both.end(), sq.begin(), sq.end());
+    both.insert(both.end(), pp.begin(), pp.end());
+    both.insert(both.end(), pq.begin(), pq.end());
     CUDA_TRY(cudaMalloc(&sk->d_sched, both.size()));
     CUDA_TRY(cudaMemcpy(sk->d_sched, both.data(), both.size(), cudaMemcpyHostToDevice));
     sk->d_sched_p = sk->d_sched;
     sk->d_sched_q = sk->d_sched + sp.size();
+    sk->d_prog_p = sk->d_sched_q + sq.size();
+    sk->d_prog_q = sk->d_prog_p + pp.size();
+    sk->tile_slots = sp[0] + 1;
+    Limbs two256 = hbn::pow2(256), inv;
+    hbn::modinv(hbn::mod(psq, two256), two256, &inv);
+    hbn::to_words(hbn::sub(two256, inv), sk->ninv_p, 8);
+    hbn::modinv(hbn::mod(qsq, two256), two256, &inv);
+    hbn::to_words(hbn::sub(two256, inv), sk->ninv_q, 8);
   }
   sk->lambda_bits = hbn::bitlen(lam);
   *out = sk.release();

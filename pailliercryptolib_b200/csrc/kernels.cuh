@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "mont_core.cuh"
+#include "mont_tile.cuh"
 
 namespace ipclb200 {
 
@@ -468,6 +469,125 @@ __global__ void __launch_bounds__(kBlockThreads)
     modexp_sched_core<K, T>(acc, x, n, m.n0inv, p.sched[side], tab);
     M::from_mont(x, acc, n, m.n0inv);
     if (valid) M::store(p.x + (inst * 2 + side) * L, x);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K4b: the same CRT-decrypt modexp for moduli of <= 2048 bits, one integer per
+// thread (mont_tile.cuh).  A CTA works on one side (even CTAs p^2, odd CTAs
+// q^2).  The whole exponentiation -- reduction of the ciphertext, table of odd
+// powers, sliding-window schedule, leaving Montgomery form -- is a byte-code
+// program built on the host (build_tile_program in ipcl_b200.cu), interpreted
+// with ONE inlined copy of the multiply:
+//   0x00        A = A^2
+//   0x01..0x3f  A = A * slot[op-1]
+//   0x40..0x7f  slot[op-0x40] = A
+//   0x80..0xbf  A = slot[op-0x80]
+//   0xc0        A = ct * R^-1      (Montgomery reduction of the 2L-limb input)
+//   0xc1        A = A * R^3 / R    (-> ct * R, Montgomery form)
+//   0xc2        A = A * R^-1       (leave Montgomery form), canonical, stop
+// Table slots live in global memory as slot[s][v][thread] (uint4), so a warp
+// reads and writes 512 contiguous bytes.
+// --------------------------------------------------------------------------
+struct DecryptTileParams {
+  const uint32_t* ct;  // count x 2L words
+  // per side (p^2, q^2): no arrays here, a runtime-indexed kernel parameter
+  // would be copied to local memory
+  ModConst m0, m1;
+  uint4 ninv0_lo, ninv0_hi, ninv1_lo, ninv1_hi;  // -N^-1 mod 2^256
+  const uint8_t *prog0, *prog1;
+  uint32_t* x;  // out: count x 2 x L words
+  size_t count;
+  uint4* table_ws;
+  int slots;
+  unsigned int* work_counter;  // zeroed before the launch
+};
+
+template <int NB, int NT>
+__global__ void __launch_bounds__(NT) decrypt_tile_kernel(const DecryptTileParams p) {
+  using TM = TileMont<NB, NT>;
+  constexpr int V = 2 * NB;
+  constexpr int L = 8 * NB;
+  extern __shared__ uint4 tile_smem[];
+  uint4* A = tile_smem;
+  uint4* B = tile_smem + V * NT;
+  uint4* QR = tile_smem + 2 * V * NT;
+  uint4* s_const = tile_smem + 3 * V * NT;  // [n0 | r3_0 | n1 | r3_1], V each
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  for (int v = tid; v < V; v += NT) {
+    s_const[v] = reinterpret_cast<const uint4*>(p.m0.n)[v];
+    s_const[V + v] = reinterpret_cast<const uint4*>(p.m0.r3)[v];
+    s_const[2 * V + v] = reinterpret_cast<const uint4*>(p.m1.n)[v];
+    s_const[3 * V + v] = reinterpret_cast<const uint4*>(p.m1.r3)[v];
+  }
+  __syncthreads();
+  // table slots of this warp: slot[s][v][lane]
+  const size_t warp_global = (size_t)blockIdx.x * (NT / 32) + (tid >> 5);
+  uint4* slot = p.table_ws + warp_global * ((size_t)p.slots * V * 32);
+  // work items: one warp-sized chunk of one side, handed out dynamically so
+  // that warps which finish early pick up the tail (the batch is ~3.5 waves
+  // of the resident threads)
+  const unsigned int nchunks = (unsigned int)((p.count + 31) / 32);
+  for (;;) {
+    unsigned int w = 0;
+    if (lane == 0) w = atomicAdd(p.work_counter, 1u);
+    w = __shfl_sync(IPCLB200_FULL_MASK, w, 0);
+    if (w >= 2u * nchunks) break;
+    const int side = (int)(w & 1u);
+    const size_t inst = (size_t)(w >> 1) * 32 + lane;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const uint4* s_n = s_const + (side ? 2 * V : 0);
+    const uint4* s_r3 = s_n + V;
+    const uint4 nl = side ? p.ninv1_lo : p.ninv0_lo, nh = side ? p.ninv1_hi : p.ninv0_hi;
+    const uint32_t ninv[8] = {nl.x, nl.y, nl.z, nl.w, nh.x, nh.y, nh.z, nh.w};
+    const uint4* c = reinterpret_cast<const uint4*>(p.ct + ii * (size_t)(2 * L));
+    const uint8_t* pc = side ? p.prog1 : p.prog0;
+#pragma unroll 1
+    for (;;) {
+      const uint32_t op = __ldg(pc++);
+      int mode;
+      if (op >= 0x40u && op < 0x80u) {  // store A
+        uint4* d = slot + (size_t)(op - 0x40u) * (V * 32);
+        for (int v = 0; v < V; v++) d[v * 32 + lane] = A[v * NT + tid];
+        continue;
+      }
+      if (op >= 0x80u && op < 0xc0u) {  // load A
+        const uint4* d = slot + (size_t)(op - 0x80u) * (V * 32);
+        for (int v = 0; v < V; v++) A[v * NT + tid] = d[v * 32 + lane];
+        continue;
+      }
+      if (op == 0x00u) {
+        mode = TM::kSqr;
+      } else if (op < 0x40u) {
+        const uint4* d = slot + (size_t)(op - 1u) * (V * 32);
+        for (int v = 0; v < V; v++) B[v * NT + tid] = d[v * 32 + lane];
+        mode = TM::kMul;
+      } else if (op == 0xc0u) {
+        for (int v = 0; v < V; v++) {
+          A[v * NT + tid] = c[v];
+          B[v * NT + tid] = c[V + v];
+        }
+        mode = TM::kRed;
+      } else if (op == 0xc1u) {
+        for (int v = 0; v < V; v++) B[v * NT + tid] = s_r3[v];
+        mode = TM::kMul;
+      } else {  // 0xc2
+        for (int v = 0; v < V; v++) B[v * NT + tid] = make_uint4(0, 0, 0, 0);
+        mode = TM::kRed;
+      }
+      TM::mont(QR, A, B, s_n, ninv, mode, tid);
+      uint4* t = A;
+      A = QR;
+      QR = t;
+      if (op == 0xc2u) break;
+    }
+    if (TM::ge_mod(A, s_n, tid)) TM::sub_mod(A, s_n, tid);
+    if (valid) {
+      uint4* o = reinterpret_cast<uint4*>(p.x + (inst * 2 + side) * L);
+      for (int v = 0; v < V; v++) o[v] = A[v * NT + tid];
+    }
   }
 }
 

@@ -5,6 +5,7 @@
 #include "ipcl/mod_exp.hpp"
 #include "ipcl/pri_key.hpp"
 #include "ipcl/utils/context.hpp"
+#include "ipcl/utils/serialize.hpp"
 
 namespace ipcl {
 

@@ -244,3 +244,26 @@ def test_homomorphic_properties_large_batch(capi, keys):
 def test_int_peak_reports(capi):
     macs, mhz = capi.int_peak()
     assert macs > 1e12 and mhz > 500
+
+
+@pytest.mark.parametrize("bits", ["1024", "2048"])
+def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
+    """the opt-in thread-per-integer decrypt kernel (mont_tile.cuh) gives the
+    same plaintexts as the default lane-distributed one"""
+    k = keys[bits]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL = int(bits) // 32
+    rng = np.random.default_rng(99)
+    count = 333
+    pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, count, NL // 2)
+    pk = capi.PubKey(to_limbs(n, NL), to_limbs(k["hs"], 2 * NL), int(bits) // 2)
+    sk = capi.PrivKey(to_limbs(p, NL // 2), to_limbs(q, NL // 2))
+    ct = pk.encrypt(pt, r)
+    base = sk.decrypt(ct)
+    monkeypatch.setenv("IPCLB200_DECRYPT", "tile")
+    alt = sk.decrypt(ct)
+    monkeypatch.delenv("IPCLB200_DECRYPT")
+    assert np.array_equal(base, pt)
+    assert np.array_equal(alt, pt)
