@@ -186,7 +186,18 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+def emit_json(line):
+    """stdout carries exactly ONE line: the JSON.  Libraries that write to the
+    C-level stdout (NCCL prints its version banner there) were redirected to
+    stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -402,7 +413,7 @@ def main():
                 "sample": "%d of 65536 elements, %s" % (args.cpu_sample, res["algo"]),
                 "encrypt_per_s": res["encrypt_per_s"],
                 "decrypt_per_s": res["decrypt_per_s"]}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
