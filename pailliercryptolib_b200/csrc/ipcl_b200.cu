@@ -268,6 +268,16 @@ int table_ws_get(void* stream, size_t words, uint32_t** out) {
   return 0;
 }
 
+// table workspace of `words` words plus the zeroed work counter behind it
+int table_ws_with_counter(cudaStream_t s, size_t words, uint32_t** ws,
+                          unsigned int** counter) {
+  words = (words + 3) & ~(size_t)3;
+  TRY(table_ws_get((void*)s, words + 4, ws));
+  *counter = reinterpret_cast<unsigned int*>(*ws + words);
+  CUDA_TRY(cudaMemsetAsync(*counter, 0, 16, s));
+  return 0;
+}
+
 int make_modulus(const Limbs& n, int L, std::shared_ptr<DevModulus>* out) {
   for (auto& m : g_ctx.mod_cache)
     if (m->L == L && m->n == n) {
@@ -323,11 +333,9 @@ int grid_for(Kern kern, size_t groups, int T, int* grid) {
   size_t need = (groups + gpb - 1) / gpb;
   size_t cap = (size_t)per_sm * g_ctx.sms;
   if (need < 1) need = 1;
-  // every group runs the same number of iterations; size the grid so the last
-  // iteration is not mostly padding (e.g. 4096 blocks of work on 592 resident:
-  // 7 iterations of 586 blocks instead of 7 of 592)
-  size_t iters = (need + cap - 1) / cap;
-  *grid = (int)((need + iters - 1) / iters);
+  // persistent grid: all resident blocks (work is claimed dynamically), or
+  // just enough blocks when the batch is smaller than one wave
+  *grid = (int)(need < cap ? need : cap);
   return 0;
 }
 
@@ -381,8 +389,8 @@ int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
   {                                                                       \
     TRY(grid_for(modexp_kernel<K_, T_>, p.count, T_, &grid));             \
     size_t groups = (size_t)grid * (kBlockThreads / T_);                  \
-    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),          \
-                     &p.table_ws));                                       \
+    TRY(table_ws_with_counter(s, groups * ((size_t)L << p.window),        \
+                              &p.table_ws, &p.work_counter));             \
     modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
   IPCLB200_DISPATCH(L, F)
@@ -647,8 +655,8 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   {                                                                        \
     TRY(grid_for(encrypt_kernel<K_, T_>, count, T_, &grid));               \
     size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
-    TRY(table_ws_get((void*)s, groups * ((size_t)L << p.window),           \
-                     &p.table_ws));                                        \
+    TRY(table_ws_with_counter(s, groups * ((size_t)L << p.window),         \
+                              &p.table_ws, &p.work_counter));              \
     encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
   IPCLB200_DISPATCH(L, F)
@@ -731,10 +739,10 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     const int L = sk->L;
     DecryptCrtParams p{};
     p.ct = d_ct;
-    p.m[0] = sk->mp2->mc;
-    p.m[1] = sk->mq2->mc;
-    p.sched[0] = sk->d_sched_p;
-    p.sched[1] = sk->d_sched_q;
+    p.m0 = sk->mp2->mc;
+    p.m1 = sk->mq2->mc;
+    p.sched0 = sk->d_sched_p;
+    p.sched1 = sk->d_sched_q;
     p.x = d_x;
     p.count = count;
     p.table_entries = 1 << (kSchedWindow - 1);
@@ -743,8 +751,8 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
   {                                                                        \
     TRY(grid_for(decrypt_crt_kernel<K_, T_>, 2 * count, T_, &grid));       \
     size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
-    TRY(table_ws_get((void*)s, groups * ((size_t)L * p.table_entries),     \
-                     &p.table_ws));                                        \
+    TRY(table_ws_with_counter(s, groups * ((size_t)L * p.table_entries),   \
+                              &p.table_ws, &p.work_counter));              \
     decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
   }
     IPCLB200_DISPATCH(L, F)

@@ -28,6 +28,16 @@ struct ModConst {
   uint32_t small_mod;   // n < R/4: canonicalise through two multiplies
 };
 
+// Dynamic work distribution: a warp claims the next chunk of 32/T consecutive
+// elements from a global counter (zeroed by the host before the launch).  The
+// batch is only a few waves of the resident groups, so a static split leaves
+// whole SMs idle during the last wave; with claims the tail is shared.
+__device__ __forceinline__ unsigned int claim_chunk(unsigned int* counter) {
+  unsigned int w = 0;
+  if ((threadIdx.x & 31) == 0) w = atomicAdd(counter, 1u);
+  return __shfl_sync(IPCLB200_FULL_MASK, w, 0);
+}
+
 // window `k` (w bits wide) of an exponent of `ew` words
 __device__ __forceinline__ uint32_t exp_window(const uint32_t* __restrict__ e,
                                                int ew, int k, int w) {
@@ -163,6 +173,7 @@ struct ModexpParams {
   size_t count;
   uint32_t* table_ws;
   int window;
+  unsigned int* work_counter;
 };
 
 template <int K, int T>
@@ -170,13 +181,15 @@ __global__ void __launch_bounds__(kBlockThreads)
     modexp_kernel(const ModexpParams p) {
   using M = Mont<K, T>;
   constexpr int L = K * T;
+  constexpr int GW = 32 / T;
   const size_t gpb = blockDim.x / T;
   const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
-  const size_t ngroups = (size_t)gridDim.x * gpb;
   uint32_t* tab = p.table_ws + gid * ((size_t)L << p.window);
-  const size_t iters = (p.count + ngroups - 1) / ngroups;
-  for (size_t it = 0; it < iters; it++) {
-    const size_t inst = it * ngroups + gid;
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= nchunks) break;
+    const size_t inst = (size_t)w * GW + (threadIdx.x & 31) / T;
     const bool valid = inst < p.count;
     const size_t ii = valid ? inst : p.count - 1;
     uint32_t n[K], x[K], acc[K];
@@ -262,6 +275,7 @@ struct EncryptParams {
   size_t count;
   uint32_t* table_ws;
   int window;
+  unsigned int* work_counter;
 };
 
 // load `words` words (zero extended to L) spread over the group
@@ -279,16 +293,18 @@ __global__ void __launch_bounds__(kBlockThreads)
     encrypt_kernel(const EncryptParams p) {
   using M = Mont<K, T>;
   constexpr int L = K * T;
+  constexpr int GW = 32 / T;
   const size_t gpb = blockDim.x / T;
   const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
-  const size_t ngroups = (size_t)gridDim.x * gpb;
   uint32_t* tab = p.table_ws + gid * ((size_t)L << p.window);
-  const size_t iters = (p.count + ngroups - 1) / ngroups;
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
   uint32_t n[K];
   M::load(n, p.m.n);
   const uint32_t n0inv = p.m.n0inv;
-  for (size_t it = 0; it < iters; it++) {
-    const size_t inst = it * ngroups + gid;
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= nchunks) break;
+    const size_t inst = (size_t)w * GW + (threadIdx.x & 31) / T;
     const bool valid = inst < p.count;
     const size_t ii = valid ? inst : p.count - 1;
     uint32_t gm[K];
@@ -420,12 +436,14 @@ __global__ void __launch_bounds__(32)
 // --------------------------------------------------------------------------
 struct DecryptCrtParams {
   const uint32_t* ct;  // count x 2L words
-  ModConst m[2];       // p^2, q^2
-  const uint8_t* sched[2];  // sliding-window schedules of p-1, q-1
+  ModConst m0, m1;     // p^2, q^2 (no arrays: a runtime-indexed kernel
+                       // parameter would be copied to local memory)
+  const uint8_t *sched0, *sched1;  // sliding-window schedules of p-1, q-1
   uint32_t* x;  // out: count x 2 x L words
   size_t count;
   uint32_t* table_ws;
   int table_entries;  // odd powers per table
+  unsigned int* work_counter;
 };
 
 template <int K, int T>
@@ -436,21 +454,22 @@ __global__ void __launch_bounds__(kBlockThreads)
   constexpr int GW = 32 / T;  // groups per warp
   const size_t gpb = blockDim.x / T;
   const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
-  const size_t ngroups = (size_t)gridDim.x * gpb;
   uint32_t* tab = p.table_ws + gid * ((size_t)L * p.table_entries);
-  // a warp works on one side only (its groups share one schedule): even
-  // warps take the p^2 tasks, odd warps the q^2 tasks
-  const int side = (int)((gid / GW) & 1);
-  const size_t sgid = (gid / (2 * GW)) * GW + gid % GW;
-  const size_t sgroups = ngroups / 2;
-  const size_t iters = (p.count + sgroups - 1) / sgroups;
-  const ModConst m = p.m[side];
-  uint32_t n[K];
-  M::load(n, m.n);
-  for (size_t it = 0; it < iters; it++) {
-    const size_t inst = it * sgroups + sgid;
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    // a chunk = the GW ciphertexts of one warp on ONE side (p^2 or q^2), so
+    // all groups of the warp follow the same schedule
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= 2u * nchunks) break;
+    const int side = (int)(w & 1u);
+    const size_t inst = (size_t)(w >> 1) * GW + (threadIdx.x & 31) / T;
     const bool valid = inst < p.count;
     const size_t ii = valid ? inst : p.count - 1;
+    const uint32_t* mn = side ? p.m1.n : p.m0.n;
+    const uint32_t* mr3 = side ? p.m1.r3 : p.m0.r3;
+    const uint32_t n0inv = side ? p.m1.n0inv : p.m0.n0inv;
+    uint32_t n[K];
+    M::load(n, mn);
     const uint32_t* c = p.ct + ii * (size_t)(2 * L);
     uint32_t x[K], acc[K];
     {
@@ -460,14 +479,14 @@ __global__ void __launch_bounds__(kBlockThreads)
 #pragma unroll
       for (int j = 0; j < K; j++) t[j] = 0;
       if (M::lane_t() == 0) t[0] = 1;
-      M::mul(lo, lo, t, n, m.n0inv);  // lo * R^-1   (<= n)
+      M::mul(lo, lo, t, n, n0inv);  // lo * R^-1   (<= n)
       uint32_t cy = M::group_add(lo, hi, 0u);  // ct * R^-1 mod n, < R + n
       if (__any_sync(IPCLB200_FULL_MASK, cy)) M::cond_sub_n(lo, n, cy);
-      M::load(t, m.r3);
-      M::mul(x, lo, t, n, m.n0inv);  // ct * R mod n: Montgomery form
+      M::load(t, mr3);
+      M::mul(x, lo, t, n, n0inv);  // ct * R mod n: Montgomery form
     }
-    modexp_sched_core<K, T>(acc, x, n, m.n0inv, p.sched[side], tab);
-    M::from_mont(x, acc, n, m.n0inv);
+    modexp_sched_core<K, T>(acc, x, n, n0inv, side ? p.sched1 : p.sched0, tab);
+    M::from_mont(x, acc, n, n0inv);
     if (valid) M::store(p.x + (inst * 2 + side) * L, x);
   }
 }
