@@ -104,6 +104,7 @@ def build_oracle(force=False):
 CPP_TEST_DIR = os.path.join(ROOT, "tests", "cpp")
 CPP_TEST_BIN = os.path.join(CPP_TEST_DIR, "_build", "ipcl_tests")
 BN_SHIM = os.path.join(CPP_TEST_DIR, "_build", "libbn_shim.so")
+BENCH_BIN = os.path.join(CPP_TEST_DIR, "_build", "bench_ipcl")
 
 
 def build_cpp_tests(force=False):
@@ -121,6 +122,11 @@ def build_cpp_tests(force=False):
         _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", CPP_TEST_BIN]
              + srcs + ["-L", LIBDIR, "-lipcl", "-lipcl_b200",
                        "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
+    bench_src = os.path.join(ROOT, "benchmarks", "bench_ipcl.cpp")
+    if os.path.exists(bench_src) and (force or not _newer(BENCH_BIN, [bench_src, IPCL_LIB])):
+        _run(["g++", "-O2", "-std=c++17"] + inc + ["-o", BENCH_BIN, bench_src,
+              "-L", LIBDIR, "-lipcl", "-lipcl_b200",
+              "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
     shim_src = os.path.join(CPP_TEST_DIR, "bn_shim.cpp")
     bn_src = os.path.join(PKG, "ipcl", "src", "bignum.cpp")
     if force or not _newer(BN_SHIM, [shim_src, bn_src,

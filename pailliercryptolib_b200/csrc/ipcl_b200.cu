@@ -633,9 +633,10 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   if (!make_secure) {
     p.mode = 0;
   } else if (pk->djn) {
-    // comb needs count large enough to amortise the table build
     const char* no_comb = getenv("IPCLB200_NO_COMB");
-    if (count >= 64 && !(no_comb && no_comb[0] == '1')) {
+    // DJN: fixed-base comb (built on first use, ~20 ms and up to 160 MB per
+    // key; IPCLB200_NO_COMB=1 keeps the generic windowed path instead)
+    if (!(no_comb && no_comb[0] == '1')) {
       TRY(build_comb(pk, r_bits > pk->rand_bits ? r_bits : pk->rand_bits, s));
       p.mode = 1;
       p.comb = pk->d_comb;

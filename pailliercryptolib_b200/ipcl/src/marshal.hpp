@@ -26,6 +26,7 @@ inline int maxWords(const std::vector<BigNumber>& v) {
 inline void pack(const std::vector<BigNumber>& v, int words,
                  std::vector<uint32_t>& out) {
   out.assign(v.size() * static_cast<std::size_t>(words), 0u);
+#pragma omp parallel for schedule(static) if (v.size() >= 4096)
   for (std::size_t i = 0; i < v.size(); i++) {
     const auto& w = v[i].words();
     if (!w.empty())
@@ -37,6 +38,7 @@ inline void pack(const std::vector<BigNumber>& v, int words,
 inline std::vector<BigNumber> unpack(const std::vector<uint32_t>& flat,
                                      std::size_t count, int words) {
   std::vector<BigNumber> r(count);
+#pragma omp parallel for schedule(static) if (count >= 4096)
   for (std::size_t i = 0; i < count; i++)
     r[i].Set(&flat[i * static_cast<std::size_t>(words)], words, IppsBigNumPOS);
   return r;

@@ -179,7 +179,18 @@ std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
   std::vector<uint32_t> f_pt, f_r, f_ct(sz * 2 * static_cast<std::size_t>(nl));
   detail::pack(*pp, nl, f_pt);
   int r_words = 0;
-  if (make_secure) {
+  if (make_secure && m_enable_DJN && !m_testv) {
+    // fresh DJN randoms (pub_key.cpp:59-61: getRandomBN(m_randbits) each):
+    // drawn straight into the flat buffer with one entropy call for the batch
+    r_words = (m_randbits + 31) / 32;
+    f_r.resize(sz * static_cast<std::size_t>(r_words));
+    rand32u(f_r);
+    if (m_randbits % 32) {
+      const uint32_t mask = (1u << (m_randbits % 32)) - 1u;
+      for (std::size_t i = 0; i < sz; i++)
+        f_r[i * static_cast<std::size_t>(r_words) + r_words - 1] &= mask;
+    }
+  } else if (make_secure) {
     std::vector<BigNumber> r = drawRandoms(sz);
     for (auto& x : r) {
       ERROR_CHECK(!x.isNegative(), "encrypt: negative random");

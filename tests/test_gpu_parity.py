@@ -161,7 +161,11 @@ def test_scheme_golden_through_cabi(capi, keys, scheme_vectors, bits, monkeypatc
     pk_djn = capi.PubKey(to_limbs(n, NL), to_limbs(hs, 2 * NL), int(bits) // 2)
     pk_std = capi.PubKey(to_limbs(n, NL))
     sk = capi.PrivKey(to_limbs(q, NL // 2), to_limbs(p, NL // 2))  # swapped on purpose
-    c_djn = pk_djn.encrypt(pt, r_djn)         # small batch: windowed hs^r
+    c_djn = pk_djn.encrypt(pt, r_djn)         # fixed-base comb for hs^r
+    monkeypatch.setenv("IPCLB200_NO_COMB", "1")
+    c_djn_win = pk_djn.encrypt(pt, r_djn)     # generic fixed-window hs^r
+    monkeypatch.delenv("IPCLB200_NO_COMB")
+    assert np.array_equal(c_djn, c_djn_win)
     c_std = pk_std.encrypt(pt, r_std)
     c_plain = pk_std.encrypt(pt, None, make_secure=False)
     assert batch_from_limbs(c_djn) == [int(i["c_djn"], 16) for i in items]

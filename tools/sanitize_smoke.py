@@ -40,10 +40,12 @@ for bits in ("1024", "2048"):
     pk = capi.PubKey(to_limbs(n, NL), to_limbs(k["hs"], 2 * NL), int(bits) // 2)
     pk0 = capi.PubKey(to_limbs(n, NL))
     sk = capi.PrivKey(to_limbs(p, NL // 2), to_limbs(q, NL // 2))
-    for count in (5, 70):           # windowed and comb obfuscator
+    for count, no_comb in ((5, "1"), (70, "0")):   # windowed and comb obfuscator
         pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
         r = random_limbs(rng, count, 2)      # short randoms keep it quick
+        os.environ["IPCLB200_NO_COMB"] = no_comb
         ct = pk.encrypt(pt, r)
+        del os.environ["IPCLB200_NO_COMB"]
         want = [(n * m + 1) * pow(k["hs"], e, n * n) % (n * n)
                 for m, e in zip(batch_from_limbs(pt), batch_from_limbs(r))]
         assert batch_from_limbs(ct) == want
