@@ -695,7 +695,7 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     p.slots = sk->tile_slots;
     constexpr int NT = 128;
     const int V = L / 4;
-    const size_t smem = (size_t)(3 * V * NT + 4 * V) * 16;
+    const size_t smem = (size_t)(2 * V * NT + 4 * V) * 16;
     int grid = 0;
 #define FT(NB_)                                                                   \
   {                                                                               \

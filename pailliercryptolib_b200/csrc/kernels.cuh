@@ -16,6 +16,9 @@
 namespace ipclb200 {
 
 constexpr int kBlockThreads = 128;
+#ifndef DECRYPT_MIN_BLOCKS
+#define DECRYPT_MIN_BLOCKS 3
+#endif
 constexpr int kMaxWindow = 6;
 
 // Per-modulus constants in device memory, each an array of L words.
@@ -447,7 +450,7 @@ struct DecryptCrtParams {
 };
 
 template <int K, int T>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
     decrypt_crt_kernel(const DecryptCrtParams p) {
   using M = Mont<K, T>;
   constexpr int L = K * T;
@@ -529,9 +532,8 @@ __global__ void __launch_bounds__(NT) decrypt_tile_kernel(const DecryptTileParam
   constexpr int L = 8 * NB;
   extern __shared__ uint4 tile_smem[];
   uint4* A = tile_smem;
-  uint4* B = tile_smem + V * NT;
-  uint4* QR = tile_smem + 2 * V * NT;
-  uint4* s_const = tile_smem + 3 * V * NT;  // [n0 | r3_0 | n1 | r3_1], V each
+  uint4* QR = tile_smem + V * NT;
+  uint4* s_const = tile_smem + 2 * V * NT;  // [n0 | r3_0 | n1 | r3_1], V each
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   for (int v = tid; v < V; v += NT) {
@@ -545,20 +547,17 @@ __global__ void __launch_bounds__(NT) decrypt_tile_kernel(const DecryptTileParam
   const size_t warp_global = (size_t)blockIdx.x * (NT / 32) + (tid >> 5);
   uint4* slot = p.table_ws + warp_global * ((size_t)p.slots * V * 32);
   // work items: one warp-sized chunk of one side, handed out dynamically so
-  // that warps which finish early pick up the tail (the batch is ~3.5 waves
-  // of the resident threads)
+  // that warps which finish early pick up the tail
   const unsigned int nchunks = (unsigned int)((p.count + 31) / 32);
   for (;;) {
-    unsigned int w = 0;
-    if (lane == 0) w = atomicAdd(p.work_counter, 1u);
-    w = __shfl_sync(IPCLB200_FULL_MASK, w, 0);
+    const unsigned int w = claim_chunk(p.work_counter);
     if (w >= 2u * nchunks) break;
     const int side = (int)(w & 1u);
     const size_t inst = (size_t)(w >> 1) * 32 + lane;
     const bool valid = inst < p.count;
     const size_t ii = valid ? inst : p.count - 1;
     const uint4* s_n = s_const + (side ? 2 * V : 0);
-    const uint4* s_r3 = s_n + V;
+    const uint4* g_r3 = reinterpret_cast<const uint4*>(side ? p.m1.r3 : p.m0.r3);
     const uint4 nl = side ? p.ninv1_lo : p.ninv0_lo, nh = side ? p.ninv1_hi : p.ninv0_hi;
     const uint32_t ninv[8] = {nl.x, nl.y, nl.z, nl.w, nh.x, nh.y, nh.z, nh.w};
     const uint4* c = reinterpret_cast<const uint4*>(p.ct + ii * (size_t)(2 * L));
@@ -566,7 +565,8 @@ __global__ void __launch_bounds__(NT) decrypt_tile_kernel(const DecryptTileParam
 #pragma unroll 1
     for (;;) {
       const uint32_t op = __ldg(pc++);
-      int mode;
+      int mode, bstride = 1;
+      const uint4* Bg = nullptr;
       if (op >= 0x40u && op < 0x80u) {  // store A
         uint4* d = slot + (size_t)(op - 0x40u) * (V * 32);
         for (int v = 0; v < V; v++) d[v * 32 + lane] = A[v * NT + tid];
@@ -580,23 +580,20 @@ __global__ void __launch_bounds__(NT) decrypt_tile_kernel(const DecryptTileParam
       if (op == 0x00u) {
         mode = TM::kSqr;
       } else if (op < 0x40u) {
-        const uint4* d = slot + (size_t)(op - 1u) * (V * 32);
-        for (int v = 0; v < V; v++) B[v * NT + tid] = d[v * 32 + lane];
+        Bg = slot + (size_t)(op - 1u) * (V * 32) + lane;
+        bstride = 32;
         mode = TM::kMul;
       } else if (op == 0xc0u) {
-        for (int v = 0; v < V; v++) {
-          A[v * NT + tid] = c[v];
-          B[v * NT + tid] = c[V + v];
-        }
+        for (int v = 0; v < V; v++) A[v * NT + tid] = c[v];
+        Bg = c + V;
         mode = TM::kRed;
       } else if (op == 0xc1u) {
-        for (int v = 0; v < V; v++) B[v * NT + tid] = s_r3[v];
+        Bg = g_r3;
         mode = TM::kMul;
       } else {  // 0xc2
-        for (int v = 0; v < V; v++) B[v * NT + tid] = make_uint4(0, 0, 0, 0);
         mode = TM::kRed;
       }
-      TM::mont(QR, A, B, s_n, ninv, mode, tid);
+      TM::mont(QR, A, Bg, bstride, s_n, ninv, mode, tid);
       uint4* t = A;
       A = QR;
       QR = t;

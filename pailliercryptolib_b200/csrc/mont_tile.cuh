@@ -13,18 +13,30 @@
 //           + 64 reduction tiles + 8 quotient blocks          = 6688 MAC32
 //   product = 64 + 64 tiles + 8 quotient blocks                = 8480 MAC32
 //
-// against 8192 for either in the CIOS form: ~16 % fewer IMAD.WIDE over a whole
+// against 8192 for either in the CIOS form: ~15 % fewer IMAD.WIDE over a whole
 // exponentiation, no shuffles, no ballots.
 //
 // Algorithm: block-level finely integrated product scanning (FIPS) with
 // 8-limb blocks.  For every column block c of the 2L-limb product all 8x8 tiles
-// (I, J), I + J = c, of the operand product and of Q*N are accumulated
-// column-wise into fifteen 96-bit column accumulators (IMAD.WIDE.U32 + one
-// IADD3.X per multiply, every column an independent chain); the quotient block
-// is Q_c = low8(W * N') with N' = -N^-1 mod 2^256; the low eight limbs are then
-// resolved, stored, and the window moves up by one block.  Results are almost
-// reduced (< R) exactly as in mont_core.cuh.  tools/model_tile_fips.py is the
-// bit-level Python model.
+// (I, J), I + J = c, of the operand product and of Q*N are accumulated into a
+// 16-limb window; the quotient block is Q_c = low8(W * N') with
+// N' = -N^-1 mod 2^256; the low eight limbs are then resolved, stored, and the
+// window moves up by one block.  Results are almost reduced (< R) exactly as in
+// mont_core.cuh.
+//
+// The window (v2; v1 used 96-bit column accumulators, one IADD3.X per multiply,
+// and was issue-bound at 2.7 instructions per multiply): even 64-bit words at
+// even limb positions and odd words at odd positions, like mont_core.cuh; a
+// tile row x_i * Y is two carry chains of four IMAD.WIDE.U32.X (even and odd
+// limbs of Y), whose carry-outs go to 32-bit counters: 64 IMAD.WIDE + 16 adds
+// per tile.  tools/model_tile_fips.py models the block algorithm,
+// tools/model_tile_eo.py the window.
+//
+// Status (round 1, B200, 2048-bit key, 65536 ciphertexts): bit-exact, 165 ms
+// against 159.5 ms for the lane-distributed kernel -- 15 % fewer multiplies but
+// only 72 % IMAD.WIDE issue utilisation (12 warps/SM fit the shared-memory
+// columns; ptxas spends another 10 % of the multiplier pipe on IMAD.MOV/IMAD.X
+// register traffic).  Opt-in with IPCLB200_DECRYPT=tile; see DESIGN.md 3.6.
 #pragma once
 #include <cstdint>
 
@@ -32,23 +44,168 @@
 
 namespace ipclb200 {
 
-// fifteen 96-bit column accumulators.  The low 64 bits are ONE 64-bit
-// register so that ptxas keeps them in an aligned pair (separate lo[]/hi[]
-// arrays made it shuffle registers with IMAD.MOV on the multiplier pipe).
-struct ColAcc {
-  uint64_t lh[15];
-  uint32_t ex[15];
+// value = sum E[u] 2^(64u) + O[u] 2^(64u+32) + cE[u] 2^(64u) + cO[u] 2^(64u+32)
+struct Win {
+  uint64_t E[8], O[8];
+  uint32_t cE[9], cO[9];
 };
 
-__device__ __forceinline__ void colacc_zero(ColAcc& w) {
+__device__ __forceinline__ void win_zero(Win& w) {
 #pragma unroll
-  for (int k = 0; k < 15; k++) {
-    w.lh[k] = 0;
-    w.ex[k] = 0;
+  for (int u = 0; u < 8; u++) {
+    w.E[u] = 0;
+    w.O[u] = 0;
+  }
+#pragma unroll
+  for (int u = 0; u < 9; u++) {
+    w.cE[u] = 0;
+    w.cO[u] = 0;
   }
 }
 
-// (ex:lh) += x * y : IMAD.WIDE.U32 with carry-out plus one IADD3.X
+// (w3:w2:w1:w0) += x * (y3, y2, y1, y0) as one carry chain; carry-out -> cnt
+__device__ __forceinline__ void chain4(uint64_t& w0, uint64_t& w1, uint64_t& w2,
+                                       uint64_t& w3, uint32_t& cnt, uint32_t x,
+                                       uint32_t y0, uint32_t y1, uint32_t y2,
+                                       uint32_t y3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mov.b64 {l3, h3}, %3;\n\t"
+      "mad.lo.cc.u32 l0, %5, %6, l0;\n\t"
+      "madc.hi.cc.u32 h0, %5, %6, h0;\n\t"
+      "madc.lo.cc.u32 l1, %5, %7, l1;\n\t"
+      "madc.hi.cc.u32 h1, %5, %7, h1;\n\t"
+      "madc.lo.cc.u32 l2, %5, %8, l2;\n\t"
+      "madc.hi.cc.u32 h2, %5, %8, h2;\n\t"
+      "madc.lo.cc.u32 l3, %5, %9, l3;\n\t"
+      "madc.hi.cc.u32 h3, %5, %9, h3;\n\t"
+      "addc.u32 %4, %4, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "mov.b64 %3, {l3, h3};\n\t"
+      "}"
+      : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3), "+r"(cnt)
+      : "r"(x), "r"(y0), "r"(y1), "r"(y2), "r"(y3));
+}
+
+// w += X * Y (8 x 8 limbs)
+__device__ __forceinline__ void tile_mac(Win& w, const uint32_t (&X)[8],
+                                         const uint32_t (&Y)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if ((i & 1) == 0) {
+      const int b = i / 2;
+      chain4(w.E[b], w.E[b + 1], w.E[b + 2], w.E[b + 3], w.cE[b + 4], X[i], Y[0],
+             Y[2], Y[4], Y[6]);
+      chain4(w.O[b], w.O[b + 1], w.O[b + 2], w.O[b + 3], w.cO[b + 4], X[i], Y[1],
+             Y[3], Y[5], Y[7]);
+    } else {
+      const int b = i / 2, b1 = (i + 1) / 2;
+      chain4(w.O[b], w.O[b + 1], w.O[b + 2], w.O[b + 3], w.cO[b + 4], X[i], Y[0],
+             Y[2], Y[4], Y[6]);
+      chain4(w.E[b1], w.E[b1 + 1], w.E[b1 + 2], w.E[b1 + 3], w.cE[b1 + 4], X[i],
+             Y[1], Y[3], Y[5], Y[7]);
+    }
+  }
+}
+
+// w += P (eight limbs at limb 0)
+__device__ __forceinline__ void win_add_block(Win& w, const uint32_t (&P)[8]) {
+  uint64_t p0 = P[0] | ((uint64_t)P[1] << 32), p1 = P[2] | ((uint64_t)P[3] << 32);
+  uint64_t p2 = P[4] | ((uint64_t)P[5] << 32), p3 = P[6] | ((uint64_t)P[7] << 32);
+  asm volatile(
+      "add.cc.u64 %0, %0, %5;\n\t"
+      "addc.cc.u64 %1, %1, %6;\n\t"
+      "addc.cc.u64 %2, %2, %7;\n\t"
+      "addc.cc.u64 %3, %3, %8;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+l"(w.E[0]), "+l"(w.E[1]), "+l"(w.E[2]), "+l"(w.E[3]), "+r"(w.cE[4])
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+}
+
+// w += P * 2^256 (eight limbs at limb 8)
+__device__ __forceinline__ void win_add_block_hi(Win& w, const uint32_t (&P)[8]) {
+  uint64_t p0 = P[0] | ((uint64_t)P[1] << 32), p1 = P[2] | ((uint64_t)P[3] << 32);
+  uint64_t p2 = P[4] | ((uint64_t)P[5] << 32), p3 = P[6] | ((uint64_t)P[7] << 32);
+  asm volatile(
+      "add.cc.u64 %0, %0, %5;\n\t"
+      "addc.cc.u64 %1, %1, %6;\n\t"
+      "addc.cc.u64 %2, %2, %7;\n\t"
+      "addc.cc.u64 %3, %3, %8;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+l"(w.E[4]), "+l"(w.E[5]), "+l"(w.E[6]), "+l"(w.E[7]), "+r"(w.cE[8])
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+}
+
+// exact low eight limbs of the window; they are cleared and their carry moves
+// to limb 8
+__device__ __forceinline__ void win_resolve_low(Win& w, uint32_t (&T)[8]) {
+  uint64_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint64_t s = carry;
+    if ((k & 1) == 0) {
+      s += (uint32_t)w.E[k / 2];
+      s += w.cE[k / 2];
+      if (k) s += (uint32_t)(w.O[k / 2 - 1] >> 32);
+    } else {
+      s += (uint32_t)(w.E[k / 2] >> 32);
+      s += (uint32_t)w.O[k / 2];
+      s += w.cO[k / 2];
+    }
+    T[k] = (uint32_t)s;
+    carry = s >> 32;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    w.E[u] = 0;
+    w.cE[u] = 0;
+    w.cO[u] = 0;
+  }
+#pragma unroll
+  for (int u = 0; u < 3; u++) w.O[u] = 0;
+  w.O[3] &= 0xffffffff00000000ull;  // its upper half is limb 8
+  uint64_t t = (uint64_t)w.cE[4] + carry;
+  w.cE[4] = (uint32_t)t;
+  w.cO[4] += (uint32_t)(t >> 32);
+}
+
+__device__ __forceinline__ void win_set_low(Win& w, const uint32_t (&T)[8]) {
+#pragma unroll
+  for (int u = 0; u < 4; u++) w.E[u] = T[2 * u] | ((uint64_t)T[2 * u + 1] << 32);
+}
+
+// window moves up by one block (the low eight limbs must be resolved)
+__device__ __forceinline__ void win_shift(Win& w) {
+  const uint32_t x = (uint32_t)(w.O[3] >> 32);
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    w.E[u] = w.E[u + 4];
+    w.O[u] = w.O[u + 4];
+    w.E[u + 4] = 0;
+    w.O[u + 4] = 0;
+  }
+#pragma unroll
+  for (int u = 0; u < 5; u++) {
+    w.cE[u] = w.cE[u + 4];
+    w.cO[u] = w.cO[u + 4];
+  }
+#pragma unroll
+  for (int u = 5; u < 9; u++) {
+    w.cE[u] = 0;
+    w.cO[u] = 0;
+  }
+  uint64_t t = (uint64_t)w.cE[0] + x;
+  w.cE[0] = (uint32_t)t;
+  w.cO[0] += (uint32_t)(t >> 32);
+}
+
+// (ex:lh) += x * y
 __device__ __forceinline__ void mac96(uint64_t& lh, uint32_t& ex, uint32_t x,
                                       uint32_t y) {
   asm volatile(
@@ -64,66 +221,7 @@ __device__ __forceinline__ void mac96(uint64_t& lh, uint32_t& ex, uint32_t x,
       : "r"(x), "r"(y));
 }
 
-// (ex:lh) += (b_ex:b_lh)
-__device__ __forceinline__ void add96(uint64_t& lh, uint32_t& ex, uint64_t b_lh,
-                                      uint32_t b_ex) {
-  asm volatile(
-      "add.cc.u64 %0, %0, %2;\n\t"
-      "addc.u32 %1, %1, %3;"
-      : "+l"(lh), "+r"(ex)
-      : "l"(b_lh), "r"(b_ex));
-}
-
-// w += X * Y (8 x 8 limbs), column k = sum of x_i*y_j with i + j = k
-__device__ __forceinline__ void tile_mac(ColAcc& w, const uint32_t (&X)[8],
-                                         const uint32_t (&Y)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-#pragma unroll
-    for (int j = 0; j < 8; j++) mac96(w.lh[i + j], w.ex[i + j], X[i], Y[j]);
-  }
-}
-
-// w += 2 * s
-__device__ __forceinline__ void colacc_add_doubled(ColAcc& w, const ColAcc& s) {
-#pragma unroll
-  for (int k = 0; k < 15; k++)
-    add96(w.lh[k], w.ex[k], s.lh[k] << 1,
-          (s.ex[k] << 1) | (uint32_t)(s.lh[k] >> 63));
-}
-
-// exact low eight limbs of the window; their carry moves into column 8 and
-// columns 0..7 are cleared
-__device__ __forceinline__ void colacc_resolve_low(ColAcc& w, uint32_t (&out)[8]) {
-  uint64_t c = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    uint64_t t = w.lh[k];
-    uint32_t e = w.ex[k];
-    add96(t, e, c, 0);
-    out[k] = (uint32_t)t;
-    c = (t >> 32) | ((uint64_t)e << 32);
-    w.lh[k] = 0;
-    w.ex[k] = 0;
-  }
-  add96(w.lh[8], w.ex[8], c, 0);
-}
-
-// window moves up by one block
-__device__ __forceinline__ void colacc_shift(ColAcc& w) {
-#pragma unroll
-  for (int k = 0; k < 7; k++) {
-    w.lh[k] = w.lh[k + 8];
-    w.ex[k] = w.ex[k + 8];
-  }
-#pragma unroll
-  for (int k = 7; k < 15; k++) {
-    w.lh[k] = 0;
-    w.ex[k] = 0;
-  }
-}
-
-// q = low eight limbs of t * ninv  (36 multiplies)
+// q = low eight limbs of t * ninv  (36 multiplies, column-wise)
 __device__ __forceinline__ void low_mul8(uint32_t (&q)[8], const uint32_t (&t)[8],
                                          const uint32_t (&ninv)[8]) {
   uint64_t a = 0;
@@ -146,12 +244,10 @@ struct TileMont {
   static constexpr int L = NB * 8;
   static constexpr int V = NB * 2;  // uint4 vectors per integer
 
-  // shared-memory accesses through 32-bit shared-window addresses (one IMAD
-  // per block instead of 64-bit generic pointer arithmetic)
   __device__ __forceinline__ static uint32_t saddr(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
   }
-  // block `blk` of an integer whose vectors are `stride` uint4 apart
+  // block `blk` of a shared-memory integer whose vectors are `stride` uint4 apart
   __device__ __forceinline__ static void ld_block(uint32_t (&x)[8], uint32_t base,
                                                   int blk, int stride) {
     uint32_t a = base + (uint32_t)(2 * blk * stride) * 16u;
@@ -170,94 +266,110 @@ struct TileMont {
                  :: "r"(a + (uint32_t)stride * 16u), "r"(x[4]), "r"(x[5]), "r"(x[6]),
                     "r"(x[7]) : "memory");
   }
+  // same from global memory (table slots, R^3, the high half of a ciphertext)
+  __device__ __forceinline__ static void ld_block_g(uint32_t (&x)[8], const uint4* base,
+                                                    int blk, int stride) {
+    uint4 a = base[(2 * blk) * stride];
+    uint4 b = base[(2 * blk + 1) * stride];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
 
-  // w += sum over I in [i0, i1) of X_I * Y_(c-I); operands of the next tile are
-  // fetched while the current one is multiplied
-  __device__ __forceinline__ static void tiles(ColAcc& w, uint32_t xb, int xs,
-                                               uint32_t yb, int ys, int c, int i0,
+  // w += sum over I in [i0, i1) of X_I * Y_(c-I).  X in shared memory; Y in
+  // shared memory (yg == nullptr) or global memory.  (Fetching the next
+  // tile's operands early was tried: the register copies it needs cost more
+  // than the latency it hides with three warps per scheduler.)
+  __device__ __forceinline__ static void tiles(Win& w, uint32_t xb, int xs, uint32_t yb,
+                                               const uint4* yg, int ys, int c, int i0,
                                                int i1) {
-    if (i0 >= i1) return;
-    uint32_t X[8], Y[8];
-    ld_block(X, xb, i0, xs);
-    ld_block(Y, yb, c - i0, ys);
 #pragma unroll 1
     for (int I = i0; I < i1; I++) {
-      uint32_t Xn[8], Yn[8];
-      const int In = I + 1 < i1 ? I + 1 : I;
-      ld_block(Xn, xb, In, xs);
-      ld_block(Yn, yb, c - In, ys);
+      uint32_t X[8], Y[8];
+      ld_block(X, xb, I, xs);
+      if (yg) ld_block_g(Y, yg, c - I, ys); else ld_block(Y, yb, c - I, ys);
       tile_mac(w, X, Y);
+    }
+  }
+
+  // w += 2 * sum over I in [i0, i1) of A_I * A_(c-I): the off-diagonal tiles of
+  // a square.  The factor two is applied to the eight-limb block A_I itself:
+  // 2*A_I = (A_I << 1 mod 2^256) + t * 2^256 with t its top bit, so the tile is
+  // multiplied with the shifted block and A_(c-I) is added one block higher
+  // when t is set -- no second window to zero, double and add per column block.
+  __device__ __forceinline__ static void tiles_dbl(Win& w, uint32_t ab, int c, int i0,
+                                                   int i1) {
+#pragma unroll 1
+    for (int I = i0; I < i1; I++) {
+      uint32_t X[8], Y[8], D[8];
+      ld_block(X, ab, I, NT);
+      ld_block(Y, ab, c - I, NT);
+      D[0] = X[0] << 1;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        X[k] = Xn[k];
-        Y[k] = Yn[k];
-      }
+      for (int k = 1; k < 8; k++) D[k] = __funnelshift_l(X[k - 1], X[k], 1);
+      tile_mac(w, D, Y);
+      const uint32_t mask = 0u - (X[7] >> 31);
+#pragma unroll
+      for (int k = 0; k < 8; k++) X[k] = Y[k] & mask;
+      win_add_block_hi(w, X);
     }
   }
 
   enum Mode { kSqr = 0, kMul = 1, kRed = 2 };
 
-  // QR = A*B/R (kMul), A*A/R (kSqr) or (A + B*R)/R (kRed: A, B are the low and
-  // high halves of a 2L-limb number).  A, B, QR: this thread's columns in
-  // shared memory (QR holds the quotient blocks first and the result after).
-  // nmod: the modulus, CTA-shared plain limbs; ninv: -N^-1 mod 2^256.
+  // QR = A*B/R (kMul), A*A/R (kSqr) or (A + B*R)/R (kRed: A and B are the low
+  // and high halves of a 2L-limb number; Bg == nullptr means B = 0).
+  // A, QR: this thread's columns in shared memory (QR holds the quotient blocks
+  // first and the result after).  Bg: operand in global memory, vectors
+  // `bstride` uint4 apart.  nmod: the modulus, CTA-shared plain limbs in shared
+  // memory; ninv: -N^-1 mod 2^256.
   __device__ __forceinline__ static void mont(uint4* QRp, const uint4* Ap,
-                                              const uint4* Bp, const uint4* nmodp,
+                                              const uint4* Bg, int bstride,
+                                              const uint4* nmodp,
                                               const uint32_t (&ninv)[8], int mode,
                                               int tid) {
-    const uint32_t A = saddr(Ap + tid), B = saddr(Bp + tid), QR = saddr(QRp + tid);
+    const uint32_t A = saddr(Ap + tid), QR = saddr(QRp + tid);
     const uint32_t nmod = saddr(nmodp);
-    ColAcc W;
-    colacc_zero(W);
+    Win W;
+    win_zero(W);
 #pragma unroll 1
     for (int c = 0; c < 2 * NB; c++) {
       if (mode == kSqr) {
-        ColAcc S;
-        colacc_zero(S);
-        tiles(S, A, NT, A, NT, c, c - NB + 1 > 0 ? c - NB + 1 : 0, (c + 1) >> 1);
-        colacc_add_doubled(W, S);
-      }
-      {
-        // tiles accumulated straight into W: the diagonal tile of a square,
-        // every operand tile of a product, nothing for a pure reduction
-        int i0, i1;
-        uint32_t yarr = B;
-        if (mode == kSqr) {
-          i0 = c >> 1;
-          i1 = ((c & 1) == 0 && (c >> 1) < NB) ? i0 + 1 : i0;
-          yarr = A;
-        } else if (mode == kMul) {
-          i0 = c - NB + 1 > 0 ? c - NB + 1 : 0;
-          i1 = (c < NB - 1 ? c : NB - 1) + 1;
-        } else {
-          i0 = i1 = 0;
-          uint32_t X[8];
-          ld_block(X, c < NB ? A : B, c < NB ? c : c - NB, NT);
-#pragma unroll
-          for (int k = 0; k < 8; k++) add96(W.lh[k], W.ex[k], (uint64_t)X[k], 0);
+        tiles_dbl(W, A, c, c - NB + 1 > 0 ? c - NB + 1 : 0, (c + 1) >> 1);
+        // diagonal tile
+        const int d = c >> 1;
+        tiles(W, A, NT, A, nullptr, NT, c, d, ((c & 1) == 0 && d < NB) ? d + 1 : d);
+      } else if (mode == kMul) {
+        tiles(W, A, NT, 0, Bg, bstride, c, c - NB + 1 > 0 ? c - NB + 1 : 0,
+              (c < NB - 1 ? c : NB - 1) + 1);
+      } else {
+        uint32_t X[8];
+        if (c < NB) {
+          ld_block(X, A, c, NT);
+          win_add_block(W, X);
+        } else if (Bg) {
+          ld_block_g(X, Bg, c - NB, bstride);
+          win_add_block(W, X);
         }
-        tiles(W, A, NT, yarr, NT, c, i0, i1);
       }
       // Q*N tiles of this column block except the one that needs Q_c itself
-      tiles(W, QR, NT, nmod, 1, c, c < NB ? 0 : c - NB + 1, c < NB ? c : NB);
+      tiles(W, QR, NT, nmod, nullptr, 1, c, c < NB ? 0 : c - NB + 1, c < NB ? c : NB);
       uint32_t T[8];
-      colacc_resolve_low(W, T);
+      win_resolve_low(W, T);
       if (c < NB) {
         uint32_t Qc[8], Y[8];
         low_mul8(Qc, T, ninv);
         st_block(QR, c, NT, Qc);
-#pragma unroll
-        for (int k = 0; k < 8; k++) W.lh[k] = T[k];
+        win_set_low(W, T);
         ld_block(Y, nmod, 0, 1);
         tile_mac(W, Qc, Y);
-        colacc_resolve_low(W, T);  // all zero by construction
+        win_resolve_low(W, T);  // all zero by construction
       } else {
         st_block(QR, c - NB, NT, T);
       }
-      colacc_shift(W);
+      win_shift(W);
     }
     // value was < R + N: bring it back below R
-    if (W.lh[0] != 0) sub_mod(QRp, nmodp, tid);
+    if ((W.E[0] | W.O[0] | W.cE[0] | W.cO[0]) != 0) sub_mod(QRp, nmodp, tid);
   }
 
   // x -= n (mod 2^(32L))
@@ -282,7 +394,6 @@ struct TileMont {
 
   // x >= n ?  (x, n: L limbs)
   __device__ __forceinline__ static bool ge_mod(const uint4* x, const uint4* nmod, int tid) {
-    bool ge = true;  // equal counts as >=
 #pragma unroll 1
     for (int v = V - 1; v >= 0; v--) {
       uint4 a = x[v * NT + tid];
@@ -292,7 +403,7 @@ struct TileMont {
       if (a.y != m.y) return a.y > m.y;
       if (a.x != m.x) return a.x > m.x;
     }
-    return ge;
+    return true;  // equal counts as >=
   }
 };
 
