@@ -68,7 +68,7 @@ def load_keys():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="add,mul,raw,key3072")
+    ap.add_argument("--only", default="add,mul,raw,key3072,cpu")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--raw-max-log2", type=int, default=20)
     ap.add_argument("--batch3072", type=int, default=262144)
@@ -175,6 +175,34 @@ def main():
                       "alg_mac32_per_op": modexp_macs(L, bits),
                       "roofline_frac_int": B * modexp_macs(L, bits) / (ms * 1e-3) / peak,
                       "hbm_gbs": B * 3 * L * 4 / (ms * 1e-3) / 1e9, "verified": "first 4 vs oracle"})
+
+    if "cpu" in only and rank == 0:
+        # CPU lines on this box's host cores, same inputs for the three
+        # implementations: scalar port, restated AVX512-IFMA mb8, OpenSSL
+        import time
+        for bits, ebits, count in ((2048, 1024, 2048), (4096, 1024, 1024)):
+            L, EL = bits // 32, ebits // 32
+            mod = random_limbs(rng, 1, L)
+            mod[0, 0] |= 1
+            mod[0, -1] |= 0x80000000
+            base, exp = random_limbs(rng, count, L), random_limbs(rng, count, EL)
+            impls = [("scalar radix-2^32 port", lambda: orc.modexp(base, exp, mod, shared_mod=True))]
+            if orc.have_ifma():
+                impls.append(("AVX512-IFMA mb8 (restated mbx_exp_mb8)",
+                              lambda: orc.modexp_mb8(base, exp, mod[0])))
+            if orc.have_openssl():
+                impls.append(("OpenSSL BN_mod_exp_mont_consttime",
+                              lambda: orc.modexp_openssl(base, exp, mod[0])))
+            ref = None
+            for name, fn in impls:
+                fn()
+                t0 = time.perf_counter()
+                out = fn()
+                dt = time.perf_counter() - t0
+                ref = out if ref is None else ref
+                assert np.array_equal(out, ref)
+                emit({"config": "CPU modexp %d-bit modulus, %d-bit exponent, %d elements" % (bits, ebits, count),
+                      "impl": name, "threads": orc.num_threads(), "modexp_per_s": count / dt})
 
     if "key3072" in only:
         k = keys["3072"]

@@ -139,3 +139,21 @@ def decrypt_crt_mb8(p, q, ct):
     if rc:
         raise ValueError("orc_decrypt_crt_mb8 rc=%d" % rc)
     return pt
+
+
+# ---- OpenSSL BN_mod_exp_mont_consttime (independent second opinion) ---------
+def have_openssl():
+    return bool(lib().orc_have_openssl())
+
+
+def modexp_openssl(base, exp, mod, shared_base=False, shared_exp=False):
+    base, exp, mod = _c(base), _c(exp), _c(mod)
+    L, EL = mod.shape[-1], exp.shape[-1]
+    count = max(np.atleast_2d(base).shape[0], np.atleast_2d(exp).shape[0])
+    out = np.zeros((count, L), dtype=np.uint32)
+    rc = lib().orc_modexp_openssl(_p(base), ctypes.c_size_t(0 if shared_base else L),
+                                  _p(exp), ctypes.c_size_t(0 if shared_exp else EL),
+                                  EL, _p(mod), L, ctypes.c_size_t(count), _p(out))
+    if rc:
+        raise ValueError("orc_modexp_openssl rc=%d" % rc)
+    return out

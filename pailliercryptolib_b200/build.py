@@ -92,7 +92,7 @@ def build_ipcl(force=False):
 def build_oracle(force=False):
     """oracle/_build/libpaillier_oracle.so -- the checker, never the product."""
     src = os.path.join(ORACLE, "paillier_oracle.c")
-    extra = [os.path.join(ORACLE, f) for f in ("ifma_modexp.c",)
+    extra = [os.path.join(ORACLE, f) for f in ("ifma_modexp.c", "openssl_modexp.c", "Makefile")
              if os.path.exists(os.path.join(ORACLE, f))]
     if not force and _newer(ORACLE_LIB, [src] + extra):
         return ORACLE_LIB

@@ -208,6 +208,7 @@ struct Ctx {
 };
 
 Ctx g_ctx;
+int g_requested_device = -1;  // set by ipclb200_init(device >= 0)
 
 int ensure_init_locked() {
   if (g_ctx.ready) {
@@ -220,7 +221,13 @@ int ensure_init_locked() {
     return fail(IPCLB200_ERR_NO_DEVICE,
                 std::string("no CUDA device: ") + cudaGetErrorString(e));
   int dev = 0;
-  if (const char* lr = getenv("LOCAL_RANK")) dev = atoi(lr) % ndev;
+  if (g_requested_device >= 0) {
+    dev = g_requested_device;
+  } else if (const char* lr = getenv("LOCAL_RANK")) {
+    dev = atoi(lr) % ndev;  // one process per GPU under torchrun
+  } else {
+    cudaGetDevice(&dev);
+  }
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10)
@@ -239,7 +246,8 @@ int ensure_init_locked() {
 int scratch_get(int slot, size_t words, uint32_t** out) {
   if (g_ctx.scratch_words[slot] < words) {
     if (g_ctx.scratch[slot]) {
-      CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+      // the *_dev entry points enqueue on caller streams: wait for all of them
+      CUDA_TRY(cudaDeviceSynchronize());
       CUDA_TRY(cudaFree(g_ctx.scratch[slot]));
       g_ctx.scratch[slot] = nullptr;
       g_ctx.scratch_words[slot] = 0;
@@ -836,9 +844,7 @@ int ipclb200_init(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev)
       return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
-    char buf[16];
-    snprintf(buf, sizeof buf, "%d", device);
-    setenv("LOCAL_RANK", buf, 1);
+    g_requested_device = device;
   }
   return ensure_init_locked();
 }

@@ -417,19 +417,6 @@ __global__ void __launch_bounds__(kBlockThreads)
   }
 }
 
-// x -> x*R mod n elementwise (used to put hs into Montgomery form)
-template <int K, int T>
-__global__ void __launch_bounds__(32)
-    to_mont_kernel(const ModConst m, const uint32_t* x, uint32_t* out) {
-  using M = Mont<K, T>;
-  uint32_t n[K], a[K], rr[K];
-  M::load(n, m.n);
-  M::load(rr, m.rr);
-  M::load(a, x);
-  M::mul(a, a, rr, n, m.n0inv);
-  if ((threadIdx.x / T) == 0) M::store(out, a);
-}
-
 // --------------------------------------------------------------------------
 // K4: fused CRT decrypt, modexp part  (PrivateKey::decryptCRT,
 //     ipcl/pri_key.cpp:114-146).  Two tasks per ciphertext (mod p^2, mod q^2),

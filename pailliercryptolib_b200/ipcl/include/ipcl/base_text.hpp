@@ -19,6 +19,8 @@ class BaseText {
   explicit BaseText(const std::vector<uint32_t>& n_v);
   explicit BaseText(const BigNumber& bn);
   explicit BaseText(const std::vector<BigNumber>& bn_v);
+  // takes ownership of a freshly unmarshalled batch (no second copy)
+  explicit BaseText(std::vector<BigNumber>&& bn_v);
   BaseText(const BaseText& bt);
   BaseText& operator=(const BaseText& other);
 

@@ -22,6 +22,7 @@ class CipherText : public BaseText {
   CipherText(const PublicKey& pk, const std::vector<uint32_t>& n_v);
   CipherText(const PublicKey& pk, const BigNumber& bn);
   CipherText(const PublicKey& pk, const std::vector<BigNumber>& bn_vec);
+  CipherText(const PublicKey& pk, std::vector<BigNumber>&& bn_vec);
   CipherText(const CipherText& ct);
   CipherText& operator=(const CipherText& other);
 

@@ -19,6 +19,7 @@ class PlainText : public BaseText {
   explicit PlainText(const std::vector<uint32_t>& n_v);
   explicit PlainText(const BigNumber& bn);
   explicit PlainText(const std::vector<BigNumber>& bn_v);
+  explicit PlainText(std::vector<BigNumber>&& bn_v);
   PlainText(const PlainText& pt);
   PlainText& operator=(const PlainText& other);
 

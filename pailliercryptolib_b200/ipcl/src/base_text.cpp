@@ -1,6 +1,8 @@
 // base_text.cpp -- ipcl::BaseText (reference: ipcl/base_text.cpp).
 #include "ipcl/base_text.hpp"
 
+#include <utility>
+
 #include "ipcl/utils/util.hpp"
 
 namespace ipcl {
@@ -17,6 +19,9 @@ BaseText::BaseText(const BigNumber& bn) : m_texts{bn}, m_size(1) {}
 
 BaseText::BaseText(const std::vector<BigNumber>& bn_v)
     : m_texts(bn_v), m_size(bn_v.size()) {}
+
+BaseText::BaseText(std::vector<BigNumber>&& bn_v)
+    : m_texts(std::move(bn_v)), m_size(m_texts.size()) {}
 
 BaseText::BaseText(const BaseText& bt)
     : m_texts(bt.m_texts), m_size(bt.m_size) {}

@@ -3,6 +3,7 @@
 #include "ipcl/ciphertext.hpp"
 
 #include <algorithm>
+#include <utility>
 
 #include "ipcl/mod_exp.hpp"
 
@@ -19,6 +20,9 @@ CipherText::CipherText(const PublicKey& pk, const BigNumber& bn)
 
 CipherText::CipherText(const PublicKey& pk, const std::vector<BigNumber>& bn_v)
     : BaseText(bn_v), m_pk(std::make_shared<PublicKey>(pk)) {}
+
+CipherText::CipherText(const PublicKey& pk, std::vector<BigNumber>&& bn_v)
+    : BaseText(std::move(bn_v)), m_pk(std::make_shared<PublicKey>(pk)) {}
 
 CipherText::CipherText(const CipherText& ct) : BaseText(ct), m_pk(ct.m_pk) {}
 

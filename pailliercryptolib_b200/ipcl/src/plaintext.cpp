@@ -2,6 +2,7 @@
 #include "ipcl/plaintext.hpp"
 
 #include <algorithm>
+#include <utility>
 
 #include "ipcl/ciphertext.hpp"
 #include "ipcl/utils/util.hpp"
@@ -12,6 +13,7 @@ PlainText::PlainText(const uint32_t& n) : BaseText(n) {}
 PlainText::PlainText(const std::vector<uint32_t>& n_v) : BaseText(n_v) {}
 PlainText::PlainText(const BigNumber& bn) : BaseText(bn) {}
 PlainText::PlainText(const std::vector<BigNumber>& bn_v) : BaseText(bn_v) {}
+PlainText::PlainText(std::vector<BigNumber>&& bn_v) : BaseText(std::move(bn_v)) {}
 PlainText::PlainText(const PlainText& pt) : BaseText(pt) {}
 
 PlainText& PlainText::operator=(const PlainText& other) {

@@ -76,7 +76,7 @@ PlainText PrivateKey::decrypt(const CipherText& ct) const {
     decryptCRT(pt_bn, ct.texts());
   else
     decryptRAW(pt_bn, ct.texts());
-  return PlainText(pt_bn);
+  return PlainText(std::move(pt_bn));
 }
 
 // both variants: pack the ciphertexts (reduced mod n^2 if a caller built an

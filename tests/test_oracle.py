@@ -139,3 +139,20 @@ def test_mb8_matches_scalar(oracle, iso, keys):
     r = random_limbs(rng, 11, 32)
     assert np.array_equal(oracle.encrypt_mb8(to_limbs(n, 64), hs, pt, r),
                           oracle.encrypt(to_limbs(n, 64), hs, pt, r))
+
+
+def test_oracle_agrees_with_openssl(oracle):
+    """third opinion: OpenSSL BN_mod_exp_mont_consttime (what the reference's
+    own QAT tests compare against, module/heqat/test/test_bnModExp.cpp:60,205)"""
+    import pytest
+    if not oracle.have_openssl():
+        pytest.skip("OpenSSL headers not installed")
+    from pailliercryptolib_b200.limbs import random_limbs
+    rng = np.random.default_rng(8)
+    for L, EL, count in [(32, 32, 24), (64, 32, 16), (128, 64, 6), (192, 48, 3)]:
+        mod = random_limbs(rng, 1, L)
+        mod[0, 0] |= 1
+        base = random_limbs(rng, count, L)
+        exp = random_limbs(rng, count, EL)
+        want = oracle.modexp_openssl(base, exp, mod[0])
+        assert np.array_equal(oracle.modexp(base, exp, mod, shared_mod=True), want)
