@@ -117,14 +117,15 @@ def build_cpp_tests(force=False):
     srcs = [os.path.join(CPP_TEST_DIR, f) for f in
             ("main.cpp", "test_cryptography.cpp", "test_ops.cpp",
              "test_serialization.cpp")]
-    deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"), IPCL_LIB]
+    deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"),
+                   os.path.join(CPP_TEST_DIR, "iso_vectors.hpp"), IPCL_LIB]
     if force or not _newer(CPP_TEST_BIN, deps):
         _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", CPP_TEST_BIN]
              + srcs + ["-L", LIBDIR, "-lipcl", "-lipcl_b200",
                        "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
     bench_src = os.path.join(ROOT, "benchmarks", "bench_ipcl.cpp")
     if os.path.exists(bench_src) and (force or not _newer(BENCH_BIN, [bench_src, IPCL_LIB])):
-        _run(["g++", "-O2", "-std=c++17"] + inc + ["-o", BENCH_BIN, bench_src,
+        _run(["g++", "-O2", "-std=c++17", "-I", CPP_TEST_DIR] + inc + ["-o", BENCH_BIN, bench_src,
               "-L", LIBDIR, "-lipcl", "-lipcl_b200",
               "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
     shim_src = os.path.join(CPP_TEST_DIR, "bn_shim.cpp")

@@ -1,21 +1,46 @@
-// base_text.cpp -- ipcl::BaseText (reference: ipcl/base_text.cpp).
+// base_text.cpp -- ipcl::BaseText, the container of BigNumbers at the API
+// boundary (interface: /root/reference/ipcl/include/ipcl/base_text.hpp:14-115;
+// error texts as in /root/reference/ipcl/base_text.cpp so callers that match on
+// them keep working).
 #include "ipcl/base_text.hpp"
 
+#include <algorithm>
 #include <utility>
 
 #include "ipcl/utils/util.hpp"
+#include "text_util.hpp"
 
 namespace ipcl {
 
-BaseText::BaseText(const uint32_t& n) : m_texts{BigNumber(n)}, m_size(1) {}
+namespace detail {
 
-BaseText::BaseText(const std::vector<uint32_t>& n_v) {
-  m_texts.reserve(n_v.size());
-  for (uint32_t n : n_v) m_texts.emplace_back(n);
-  m_size = m_texts.size();
+std::vector<BigNumber> rotated(const std::vector<BigNumber>& v, int shift) {
+  const int size = static_cast<int>(v.size());
+  ERROR_CHECK(size != 1, "rotate: Cannot rotate single CipherText");
+  ERROR_CHECK(shift >= -size && shift <= size,
+              "rotate: Cannot shift more than the test size");
+  std::vector<BigNumber> out(v);
+  if (size == 0 || shift % size == 0) return out;
+  // a positive shift moves element i to i + shift
+  const int left = shift > 0 ? size - shift : -shift;
+  std::rotate(out.begin(), out.begin() + left, out.end());
+  return out;
 }
 
-BaseText::BaseText(const BigNumber& bn) : m_texts{bn}, m_size(1) {}
+}  // namespace detail
+
+#define TEXT_INDEX_CHECK(i, what) \
+  ERROR_CHECK((i) < m_size, "BaseText: " what " index is out of range")
+
+BaseText::BaseText(const uint32_t& n) : m_texts(1, BigNumber(n)), m_size(1) {}
+
+BaseText::BaseText(const std::vector<uint32_t>& n_v) : m_size(n_v.size()) {
+  m_texts.reserve(m_size);
+  std::transform(n_v.begin(), n_v.end(), std::back_inserter(m_texts),
+                 [](uint32_t w) { return BigNumber(w); });
+}
+
+BaseText::BaseText(const BigNumber& bn) : m_texts(1, bn), m_size(1) {}
 
 BaseText::BaseText(const std::vector<BigNumber>& bn_v)
     : m_texts(bn_v), m_size(bn_v.size()) {}
@@ -23,8 +48,7 @@ BaseText::BaseText(const std::vector<BigNumber>& bn_v)
 BaseText::BaseText(std::vector<BigNumber>&& bn_v)
     : m_texts(std::move(bn_v)), m_size(m_texts.size()) {}
 
-BaseText::BaseText(const BaseText& bt)
-    : m_texts(bt.m_texts), m_size(bt.m_size) {}
+BaseText::BaseText(const BaseText& bt) : m_texts(bt.m_texts), m_size(bt.m_size) {}
 
 BaseText& BaseText::operator=(const BaseText& other) {
   if (this != &other) {
@@ -39,48 +63,48 @@ BigNumber& BaseText::operator[](const std::size_t idx) {
   return m_texts[idx];
 }
 
+BigNumber BaseText::getElement(const std::size_t& idx) const {
+  TEXT_INDEX_CHECK(idx, "getElement");
+  return m_texts[idx];
+}
+
+std::vector<uint32_t> BaseText::getElementVec(const std::size_t& idx) const {
+  TEXT_INDEX_CHECK(idx, "getElementVec");
+  std::vector<uint32_t> words;
+  m_texts[idx].num2vec(words);
+  return words;
+}
+
+std::string BaseText::getElementHex(const std::size_t& idx) const {
+  TEXT_INDEX_CHECK(idx, "getElementHex");
+  std::string hex;
+  m_texts[idx].num2hex(hex);
+  return hex;
+}
+
+std::vector<BigNumber> BaseText::getChunk(const std::size_t& start,
+                                          const std::size_t& size) const {
+  ERROR_CHECK(start + size <= m_size, "BaseText: getChunk parameter is incorrect");
+  return {m_texts.begin() + static_cast<std::ptrdiff_t>(start),
+          m_texts.begin() + static_cast<std::ptrdiff_t>(start + size)};
+}
+
 void BaseText::insert(const std::size_t pos, BigNumber& bn) {
   ERROR_CHECK(pos <= m_size, "BaseText: insert position is out of range");
   m_texts.insert(m_texts.begin() + static_cast<std::ptrdiff_t>(pos), bn);
-  m_size++;
+  m_size = m_texts.size();
+}
+
+void BaseText::remove(const std::size_t pos, const std::size_t length) {
+  ERROR_CHECK(pos + length < m_size, "BaseText: remove position is out of range");
+  const auto first = m_texts.begin() + static_cast<std::ptrdiff_t>(pos);
+  m_texts.erase(first, first + static_cast<std::ptrdiff_t>(length));
+  m_size = m_texts.size();
 }
 
 void BaseText::clear() {
   m_texts.clear();
   m_size = 0;
-}
-
-void BaseText::remove(const std::size_t pos, const std::size_t length) {
-  ERROR_CHECK(pos + length < m_size, "BaseText: remove position is out of range");
-  auto first = m_texts.begin() + static_cast<std::ptrdiff_t>(pos);
-  m_texts.erase(first, first + static_cast<std::ptrdiff_t>(length));
-  m_size -= length;
-}
-
-BigNumber BaseText::getElement(const std::size_t& idx) const {
-  ERROR_CHECK(idx < m_size, "BaseText: getElement index is out of range");
-  return m_texts[idx];
-}
-
-std::vector<uint32_t> BaseText::getElementVec(const std::size_t& idx) const {
-  ERROR_CHECK(idx < m_size, "BaseText: getElementVec index is out of range");
-  std::vector<uint32_t> v;
-  m_texts[idx].num2vec(v);
-  return v;
-}
-
-std::string BaseText::getElementHex(const std::size_t& idx) const {
-  ERROR_CHECK(idx < m_size, "BaseText: getElementHex index is out of range");
-  std::string s;
-  m_texts[idx].num2hex(s);
-  return s;
-}
-
-std::vector<BigNumber> BaseText::getChunk(const std::size_t& start,
-                                          const std::size_t& size) const {
-  ERROR_CHECK((start + size) <= m_size, "BaseText: getChunk parameter is incorrect");
-  auto first = m_texts.begin() + static_cast<std::ptrdiff_t>(start);
-  return std::vector<BigNumber>(first, first + static_cast<std::ptrdiff_t>(size));
 }
 
 std::vector<BigNumber> BaseText::getTexts() const { return m_texts; }

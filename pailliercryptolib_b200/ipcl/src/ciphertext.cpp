@@ -6,6 +6,7 @@
 #include <utility>
 
 #include "ipcl/mod_exp.hpp"
+#include "text_util.hpp"
 
 namespace ipcl {
 
@@ -72,16 +73,7 @@ CipherText CipherText::getCipherText(const size_t& idx) const {
 std::shared_ptr<PublicKey> CipherText::getPubKey() const { return m_pk; }
 
 CipherText CipherText::rotate(int shift) const {
-  const int size = static_cast<int>(m_size);
-  ERROR_CHECK(m_size != 1, "rotate: Cannot rotate single CipherText");
-  ERROR_CHECK(shift >= -size && shift <= size,
-              "rotate: Cannot shift more than the test size");
-  if (shift == 0 || shift == size || shift == -size)
-    return CipherText(*m_pk, m_texts);
-  const int left = shift > 0 ? size - shift : -shift;
-  std::vector<BigNumber> v(m_texts);
-  std::rotate(v.begin(), v.begin() + left, v.end());
-  return CipherText(*m_pk, v);
+  return CipherText(*m_pk, detail::rotated(m_texts, shift));
 }
 
 BigNumber CipherText::raw_add(const BigNumber& a, const BigNumber& b) const {

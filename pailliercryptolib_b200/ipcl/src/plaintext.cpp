@@ -1,11 +1,14 @@
-// plaintext.cpp -- ipcl::PlainText (reference: ipcl/plaintext.cpp).
+// plaintext.cpp -- ipcl::PlainText (interface:
+// /root/reference/ipcl/include/ipcl/plaintext.hpp:18-98).  A PlainText is a
+// BaseText plus conversions and the commuted forms of the homomorphic
+// operators, which simply forward to CipherText.
 #include "ipcl/plaintext.hpp"
 
-#include <algorithm>
 #include <utility>
 
 #include "ipcl/ciphertext.hpp"
 #include "ipcl/utils/util.hpp"
+#include "text_util.hpp"
 
 namespace ipcl {
 
@@ -21,24 +24,19 @@ PlainText& PlainText::operator=(const PlainText& other) {
   return *this;
 }
 
-CipherText PlainText::operator+(const CipherText& other) const {
-  return other.operator+(*this);
-}
+// pt + ct and pt * ct commute with the CipherText forms
+CipherText PlainText::operator+(const CipherText& ct) const { return ct + *this; }
+CipherText PlainText::operator*(const CipherText& ct) const { return ct * *this; }
 
-CipherText PlainText::operator*(const CipherText& other) const {
-  return other.operator*(*this);
-}
-
+// conversions of the FIRST element (and of the whole container)
 PlainText::operator std::vector<uint32_t>() const {
   ERROR_CHECK(m_size > 0, "PlainText: type conversion to uint32_t vector error");
-  std::vector<uint32_t> v;
-  m_texts[0].num2vec(v);
-  return v;
+  return getElementVec(0);
 }
 
 PlainText::operator BigNumber() const {
   ERROR_CHECK(m_size > 0, "PlainText: type conversion to BigNumber error");
-  return m_texts[0];
+  return m_texts.front();
 }
 
 PlainText::operator std::vector<BigNumber>() const {
@@ -47,16 +45,7 @@ PlainText::operator std::vector<BigNumber>() const {
 }
 
 PlainText PlainText::rotate(int shift) const {
-  const int size = static_cast<int>(m_size);
-  ERROR_CHECK(m_size != 1, "rotate: Cannot rotate single CipherText");
-  ERROR_CHECK(shift >= -size && shift <= size,
-              "rotate: Cannot shift more than the test size");
-  if (shift == 0 || shift == size || shift == -size) return PlainText(m_texts);
-  // positive shift moves elements towards higher indices
-  const int left = shift > 0 ? size - shift : -shift;
-  std::vector<BigNumber> v(m_texts);
-  std::rotate(v.begin(), v.begin() + left, v.end());
-  return PlainText(v);
+  return PlainText(detail::rotated(m_texts, shift));
 }
 
 }  // namespace ipcl
