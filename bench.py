@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-sample", type=int, default=4096,
+    ap.add_argument("--cpu-sample", type=int, default=16384,
                     help="elements of the workload timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -353,6 +353,8 @@ def main():
                 traffic = json.load(f).get("decrypt_crt_kernel_dram_bytes")
         except Exception:
             pass
+        comb_w = int(os.environ.get("IPCLB200_COMB_WINDOW", "16"))
+        comb_products = (KEY_BITS // 2 + comb_w - 1) // comb_w - 1 + 3
         ach = B * MAC_DECRYPT / dec_s / 1e12
         roofline = {
             "kernel": "decrypt_crt_kernel<16,4> (2 x 2048-bit-modulus, "
@@ -371,14 +373,15 @@ def main():
                     "frac": B * BYTES_DECRYPT / dec_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src},
             "encrypt_kernel": {
-                "kernel": "encrypt_kernel<16,8> (fixed-base comb for hs^r, 11-bit windows)",
+                "kernel": "encrypt_kernel<16,8> (fixed-base comb for hs^r)",
                 "achieved": B * MAC_ENCRYPT / enc_s / 1e12, "unit": "TMAC32/s",
                 "frac": B * MAC_ENCRYPT / enc_s / peak_mac,
                 "note": "algorithmic count is the generic w=5 windowed modexp "
-                        "(41.55 M MAC32); the comb kernel (11-bit windows) executes "
-                        "97 Montgomery products (3.18 M MAC32), so frac > 1 is the "
-                        "algorithm, not the pipe",
-                "executed_frac": B * 97 * 2 * (2 * NL) ** 2 / enc_s / peak_mac,
+                        "(41.55 M MAC32); the comb kernel (%d-bit windows) executes "
+                        "%d Montgomery products (%.2f M MAC32), so frac > 1 is the "
+                        "algorithm, not the pipe" % (comb_w, comb_products,
+                                                     comb_products * 2 * (2 * NL) ** 2 / 1e6),
+                "executed_frac": B * comb_products * 2 * (2 * NL) ** 2 / enc_s / peak_mac,
                 "launch_ms": enc_mean,
             },
         }

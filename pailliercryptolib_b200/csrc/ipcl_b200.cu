@@ -575,39 +575,61 @@ int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
 int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
   const int L = pk->L;
   if (pk->d_comb && pk->comb_windows * pk->comb_w >= bits) return 0;
-  // widest window (<= 11 bits) whose table stays under 160 MB: 1024-bit r at
-  // a 2048-bit key -> w = 11, 94 windows x 2048 entries x 512 B = 98 MB
-  // (measured on B200: w = 8/9/10/11 -> 40.4/36.0/32.6/30.1 ms per 65536)
-  int w = 11;
-  while (w > 4 && (size_t)((bits + w - 1) / w) * ((size_t)L << w) * 4 > (160u << 20)) w--;
+  // Widest window (<= 16 bits) whose table fits the budget.  B200 has 180 GB of
+  // HBM and the kernel needs one 4L-byte entry per window and element, so the
+  // table can be large: 1024-bit r at a 2048-bit key, w = 16 -> 64 windows x
+  // 65536 entries x 512 B = 2.1 GB and 64 multiplies per encryption.
+  // Measured on B200, ms per 65536 encryptions: w = 8/9/10/11 -> 40.4/36.0/
+  // 32.6/30.1 (static split); see DESIGN.md for the wider ones.
+  size_t budget_mb = 4096;
+  if (const char* e = getenv("IPCLB200_COMB_MAX_MB")) budget_mb = strtoul(e, nullptr, 10);
+  int w = 16;
+  auto table_words = [&](int ww) {
+    return (size_t)((bits + ww - 1) / ww) * ((size_t)L << ww);
+  };
+  while (w > 4 && table_words(w) * 4 > (budget_mb << 20)) w--;
   if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
     int v = atoi(cw);
-    if (v >= 1 && v <= 12) w = v;
+    if (v >= 1 && v <= 16) w = v;
   }
-  int windows = (bits + w - 1) / w;
-  if (windows < 1) windows = 1;
   if (pk->d_comb) {
-    // a wider exponent than the table covers: rebuild with the width the new
-    // size allows (keeps comb_w consistent with the table in memory)
+    // a wider exponent than the table covers: rebuild
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaFree(pk->d_comb));
     pk->d_comb = nullptr;
     pk->comb_windows = 0;
   }
-  size_t words = (size_t)windows * ((size_t)L << w);
-  CUDA_TRY(cudaMalloc(&pk->d_comb, words * sizeof(uint32_t)));
+  // back off to narrower windows if the allocation does not fit
+  for (;; w--) {
+    cudaError_t e = cudaMalloc(&pk->d_comb, table_words(w) * sizeof(uint32_t));
+    if (e == cudaSuccess) break;
+    cudaGetLastError();
+    pk->d_comb = nullptr;
+    if (w <= 4) return fail(IPCLB200_ERR_CUDA, "cannot allocate the fixed-base table");
+  }
+  int windows = (bits + w - 1) / w;
+  if (windows < 1) windows = 1;
   CombParams cp{};
   cp.m = pk->msq->mc;
   cp.hs_m = pk->d_const + L;
   cp.comb = pk->d_comb;
   cp.w = w;
+  cp.w_lo = w > 11 ? (w + 1) / 2 : w;  // two-level build for wide windows
   cp.windows = windows;
+  const int nchains = cp.w_lo < w ? 2 * windows : windows;
 #define F(K_, T_)                                                       \
   {                                                                     \
     comb_spine_kernel<K_, T_><<<1, 32, 0, s>>>(cp);                     \
     int gpb = kBlockThreads / T_;                                       \
-    int grid = (windows + gpb - 1) / gpb;                               \
+    int grid = (nchains + gpb - 1) / gpb;                               \
     comb_fill_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(cp);        \
+    if (cp.w_lo < w) {                                                  \
+      int eg = 0;                                                       \
+      TRY(grid_for(comb_expand_kernel<K_, T_>,                          \
+                   (size_t)windows << w, T_, &eg));                     \
+      comb_expand_kernel<K_, T_><<<eg, kBlockThreads, 0, s>>>(cp);      \
+      g_ctx.launches++;                                                 \
+    }                                                                   \
   }
   IPCLB200_DISPATCH(L, F)
 #undef F

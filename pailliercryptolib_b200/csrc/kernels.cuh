@@ -374,7 +374,8 @@ struct CombParams {
   ModConst m;
   const uint32_t* hs_m;  // hs in Montgomery form
   uint32_t* comb;
-  int w;
+  int w;     // window width, entries per window = 2^w
+  int w_lo;  // two-level build: entry j = (b << w_lo) | a is row[b << w_lo] * row[a]
   int windows;
 };
 
@@ -390,10 +391,18 @@ __global__ void __launch_bounds__(32) comb_spine_kernel(const CombParams p) {
   const size_t wstride = (size_t)L << p.w;
   for (int i = 0; i < p.windows; i++) {
     if (writer) M::store(p.comb + (size_t)i * wstride + L, g);
-    for (int s = 0; s < p.w; s++) M::mul(g, g, g, n, p.m.n0inv);
+    for (int s = 0; s < p.w; s++) {
+      M::mul(g, g, g, n, p.m.n0inv);
+      // g_i^(2^w_lo): the generator of the upper chain of window i
+      if (writer && s + 1 == p.w_lo && p.w_lo < p.w)
+        M::store(p.comb + (size_t)i * wstride + ((size_t)L << p.w_lo), g);
+    }
   }
 }
 
+// level 1: the two sequential chains of each window, one group per chain:
+//   lower  row[a]         = g^a            a < 2^w_lo   (row[1] = g given)
+//   upper  row[b << w_lo] = (g^(2^w_lo))^b b < 2^(w - w_lo)
 template <int K, int T>
 __global__ void __launch_bounds__(kBlockThreads)
     comb_fill_kernel(const CombParams p) {
@@ -401,19 +410,57 @@ __global__ void __launch_bounds__(kBlockThreads)
   constexpr int L = K * T;
   const int gpb = blockDim.x / T;
   const int gid = blockIdx.x * gpb + threadIdx.x / T;
-  const bool valid = gid < p.windows;
-  const int i = valid ? gid : p.windows - 1;
+  const bool two = p.w_lo < p.w;
+  const int nchains = two ? 2 * p.windows : p.windows;
+  const bool valid = gid < nchains;
+  const int ch = valid ? gid : nchains - 1;
+  const int i = two ? ch >> 1 : ch;
+  const bool upper = two && (ch & 1);
+  const size_t step = upper ? ((size_t)1 << p.w_lo) : 1;
+  const int count = upper ? (1 << (p.w - p.w_lo)) : (1 << p.w_lo);
   uint32_t* row = p.comb + (size_t)i * ((size_t)L << p.w);
   uint32_t n[K], g[K], t[K];
   M::load(n, p.m.n);
-  M::load(g, row + L);
-  M::load(t, p.m.one);
-  if (valid) M::store(row, t);
+  M::load(g, row + step * L);
+  if (!upper) {
+    M::load(t, p.m.one);
+    if (valid) M::store(row, t);
+  }
 #pragma unroll
   for (int j = 0; j < K; j++) t[j] = g[j];
-  for (int j = 2; j < (1 << p.w); j++) {
+  for (int j = 2; j < count; j++) {
     M::mul(t, t, g, n, p.m.n0inv);
-    if (valid) M::store(row + (size_t)j * L, t);
+    if (valid) M::store(row + (size_t)j * step * L, t);
+  }
+}
+
+// level 2: every remaining entry is one product of a lower and an upper entry
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads)
+    comb_expand_kernel(const CombParams p) {
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  const size_t ngroups = (size_t)gridDim.x * gpb;
+  const size_t per_win = (size_t)1 << p.w;
+  const size_t total = per_win * (size_t)p.windows;
+  const size_t lo_mask = ((size_t)1 << p.w_lo) - 1;
+  uint32_t n[K];
+  M::load(n, p.m.n);
+  const size_t iters = (total + ngroups - 1) / ngroups;
+  for (size_t it = 0; it < iters; it++) {
+    const size_t e = it * ngroups + gid;
+    const bool in = e < total;
+    const size_t ee = in ? e : total - 1;
+    const size_t j = ee & (per_win - 1);
+    uint32_t* row = p.comb + (ee >> p.w) * (per_win * L);
+    const bool need = in && (j & lo_mask) != 0 && (j & ~lo_mask) != 0;
+    uint32_t a[K], b[K];
+    M::load(a, row + (j & lo_mask) * L);
+    M::load(b, row + (j & ~lo_mask) * L);
+    M::mul(a, a, b, n, p.m.n0inv);
+    if (need) M::store(row + j * L, a);
   }
 }
 
