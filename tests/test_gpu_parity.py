@@ -271,3 +271,41 @@ def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     monkeypatch.delenv("IPCLB200_DECRYPT")
     assert np.array_equal(base, pt)
     assert np.array_equal(alt, pt)
+
+
+def test_concurrent_callers_through_cabi(capi, keys):
+    """the C ABI is re-entrant: four host threads encrypt and decrypt on the
+    same key objects at once (the reference calls encrypt/decrypt concurrently
+    on one key, test/test_cryptography.cpp:45-57); ctypes drops the GIL"""
+    import threading
+    k = keys["1024"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL = 32
+    pk = capi.PubKey(to_limbs(n, NL), to_limbs(k["hs"], 2 * NL), 512)
+    sk = capi.PrivKey(to_limbs(p, NL // 2), to_limbs(q, NL // 2))
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(3):
+                count = int(rng.integers(1, 300))
+                pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+                r = random_limbs(rng, count, NL // 2)
+                ct = pk.encrypt(pt, r)
+                if not np.array_equal(sk.decrypt(ct), pt):
+                    errors.append("round trip %d" % seed)
+                m = capi.modmul(ct, ct, to_limbs(n * n, 2 * NL))
+                d = batch_from_limbs(sk.decrypt(m))
+                if d != [2 * x % n for x in batch_from_limbs(pt)]:
+                    errors.append("ct+ct %d" % seed)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
