@@ -309,3 +309,35 @@ def test_concurrent_callers_through_cabi(capi, keys):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_full_size_batch_65536(capi, keys):
+    """BASELINE.json configs[1]/[2] at full size (2048-bit key, 65536 elements),
+    checked through size-independent properties: decrypt(encrypt(m)) == m for
+    every element, decrypt(ct_a * ct_b mod n^2) == a + b, and the ciphertexts
+    of two different randoms for the same plaintext differ"""
+    k = keys["2048"]
+    p, q = k["p"], k["q"]
+    n = p * q
+    NL, count = 64, 65536
+    rng = np.random.default_rng(65536)
+    a = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    b = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    pk = capi.PubKey(to_limbs(n, NL), to_limbs(k["hs"], 2 * NL), 1024)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    ca = pk.encrypt(a, random_limbs(rng, count, 32))
+    ca2 = pk.encrypt(a, random_limbs(rng, count, 32))
+    cb = pk.encrypt(b, random_limbs(rng, count, 32))
+    assert np.array_equal(sk.decrypt(ca), a)
+    assert np.array_equal(sk.decrypt(ca2), a)
+    assert not np.array_equal(ca, ca2)
+    s = sk.decrypt(capi.modmul(ca, cb, to_limbs(n * n, 128)))
+    # a, b < 2^2046 so a + b < n: plain multi-limb sum
+    t = a.astype(np.uint64) + b.astype(np.uint64)
+    want = np.zeros_like(a)
+    carry = np.zeros(count, dtype=np.uint64)
+    for j in range(NL):
+        v = t[:, j] + carry
+        want[:, j] = (v & 0xFFFFFFFF).astype(np.uint32)
+        carry = v >> 32
+    assert np.array_equal(s, want)
