@@ -156,6 +156,23 @@ int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
 int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz);
 uint64_t ipclb200_launch_count(void);
 
+/* Pipe-overlap probe (profiles/r01_pipe_overlap.md): time of a fixed number of
+ * IMAD.WIDE chains (mode 0), DFMA chains (1), both kinds on every SM
+ * sub-partition at once (2), and each half of mode 2 alone (3: integer half,
+ * 4: DFMA half).  Tells whether the FP64 pipe can work beside the integer
+ * multiply pipe. */
+int ipclb200_pipe_mix(int mode, double* ms_out);
+
+/* Diagnostics: the two CRT residues of every ciphertext,
+ *   x[i][0] = ct[i]^(p-1) mod p^2,  x[i][1] = ct[i]^(q-1) mod q^2
+ * (the modexp results of ipcl/pri_key.cpp:128-134, before the L function), as
+ * the decrypt kernel -- whichever pipe(s) IPCLB200_DECRYPT selects -- left
+ * them.  x: count x 2 x *x_words words; *x_words is the kernel size class of
+ * p^2 (>= 2*p_words).  Used by the parity tests to check the integer-pipe and
+ * FP64-pipe kernels against the oracle independently of the CRT tail. */
+int ipclb200_crt_residues(const ipclb200_privkey* sk, const uint32_t* ct,
+                          size_t count, uint32_t* x, int* x_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,8 @@ EXPORTS = [
     "ipclb200_pubkey_create", "ipclb200_pubkey_destroy", "ipclb200_encrypt",
     "ipclb200_encrypt_dev", "ipclb200_privkey_create",
     "ipclb200_privkey_destroy", "ipclb200_decrypt", "ipclb200_decrypt_dev",
-    "ipclb200_int_peak", "ipclb200_launch_count",
+    "ipclb200_int_peak", "ipclb200_launch_count", "ipclb200_crt_residues",
+    "ipclb200_pipe_mix",
 ]
 
 
@@ -90,6 +91,12 @@ def int_peak():
     macs, mhz = ctypes.c_double(), ctypes.c_double()
     _check(lib().ipclb200_int_peak(ctypes.byref(macs), ctypes.byref(mhz)))
     return macs.value, mhz.value
+
+
+def pipe_mix(mode):
+    ms = ctypes.c_double()
+    _check(lib().ipclb200_pipe_mix(int(mode), ctypes.byref(ms)))
+    return ms.value
 
 
 def modexp(base, exp, mod, flags=0):
@@ -171,6 +178,20 @@ class PrivKey:
         _check(lib().ipclb200_decrypt(self._h, _p(ct), ctypes.c_size_t(ct.shape[0]),
                                       int(use_crt), _p(pt)))
         return pt
+
+    def crt_residues(self, ct):
+        """(count, 2, class words) array: ct^(p-1) mod p^2 and ct^(q-1) mod q^2
+        as the decrypt kernel left them (diagnostics for the parity tests)"""
+        ct = np.atleast_2d(_c(ct))
+        assert ct.shape[1] == 4 * self.p_words
+        xw = ctypes.c_int()
+        _check(lib().ipclb200_crt_residues(self._h, _p(ct), ctypes.c_size_t(0),
+                                           _p(ct), ctypes.byref(xw)))
+        x = np.zeros((ct.shape[0], 2, xw.value), dtype=np.uint32)
+        _check(lib().ipclb200_crt_residues(self._h, _p(ct),
+                                           ctypes.c_size_t(ct.shape[0]), _p(x),
+                                           ctypes.byref(xw)))
+        return x
 
     def decrypt_dev(self, d_ct, count, d_pt, stream, use_crt=True):
         _check(lib().ipclb200_decrypt_dev(self._h, _vp(d_ct), ctypes.c_size_t(count),

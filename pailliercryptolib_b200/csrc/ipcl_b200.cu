@@ -150,6 +150,24 @@ std::vector<uint8_t> build_schedule(const Limbs& e, int w) {
   return s;
 }
 
+// FP64 role (mont_fp64.cuh): the 64-word class (p^2 of a 2048-bit key) as 96
+// limbs of 22 bits over 4 lanes
+constexpr int kFpWords = 64;
+constexpr int kFpK = 24, kFpT = 4;
+constexpr int kFpLimbs = kFpK * kFpT;
+
+void fp_limbs(const Limbs& x, double* out, int L) {
+  for (int g = 0; g < L; g++) {
+    const unsigned off = (unsigned)kFpW * (unsigned)g;
+    const size_t idx = off / 32;
+    const unsigned sh = off % 32;
+    uint64_t v = 0;
+    if (idx < x.size()) v = x[idx];
+    if (idx + 1 < x.size()) v |= (uint64_t)x[idx + 1] << 32;
+    out[g] = (double)((v >> sh) & kFpMask);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // per-modulus constants
 // ---------------------------------------------------------------------------
@@ -196,6 +214,9 @@ struct Ctx {
   int device = -1;
   int sms = 0;
   cudaStream_t stream = nullptr;
+  // second stream + events for the two-kernel dual-pipe decrypt
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // grow-only scratch buffers for the host-pointer entry points
   static const int kSlots = 8;
   uint32_t* scratch[kSlots] = {};
@@ -237,6 +258,9 @@ int ensure_init_locked() {
                     ", this library holds sm_100a code only");
   CUDA_TRY(cudaSetDevice(dev));
   CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.aux_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
   g_ctx.device = dev;
   g_ctx.sms = prop.multiProcessorCount;
   g_ctx.ready = true;
@@ -278,9 +302,9 @@ int table_ws_get(void* stream, size_t words, uint32_t** out) {
 
 // table workspace of `words` words plus the zeroed work counter behind it
 int table_ws_with_counter(cudaStream_t s, size_t words, uint32_t** ws,
-                          unsigned int** counter) {
+                          unsigned int** counter, int key = 0) {
   words = (words + 3) & ~(size_t)3;
-  TRY(table_ws_get((void*)s, words + 4, ws));
+  TRY(table_ws_get((void*)((uintptr_t)s + (uintptr_t)key), words + 4, ws));
   *counter = reinterpret_cast<unsigned int*>(*ws + words);
   CUDA_TRY(cudaMemsetAsync(*counter, 0, 16, s));
   return 0;
@@ -467,9 +491,14 @@ struct ipclb200_privkey {
   const uint8_t *d_prog_p = nullptr, *d_prog_q = nullptr;
   uint32_t ninv_p[8] = {}, ninv_q[8] = {};
   int tile_slots = 0;
+  // FP64-pipe constants (mont_fp64.cuh), only for the 64-word class of p^2
+  double* d_fp = nullptr;
+  FpModConst fp0{}, fp1{};
+  bool fp_ok = false;
   ~ipclb200_privkey() {
     if (d_const) cudaFree(d_const);
     if (d_sched) cudaFree(d_sched);
+    if (d_fp) cudaFree(d_fp);
   }
 };
 
@@ -777,7 +806,108 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     p.x = d_x;
     p.count = count;
     p.table_entries = 1 << (kSchedWindow - 1);
-    int grid = 0;
+    // which pipes: "int" = integer kernel only, "fp" = FP64 kernel only,
+    // "dual" = both roles in one kernel, "dual2" = two kernels on two streams
+    // sharing the work counter.  FP64 needs the 64-word class (2048-bit key).
+    const char* mode = force ? force : "int";
+    const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
+               want_dual2 = !strcmp(mode, "dual2");
+    if ((want_fp || want_dual || want_dual2) && sk->fp_ok && L == kFpWords) {
+      constexpr int FL = kFpLimbs;
+      constexpr size_t smem = fp_role_smem(kFpK, kFpT);
+      const int sms = g_ctx.sms;
+      const size_t chunks = 2 * ((count + 7) / 8);          // warps of work
+      const size_t need = (chunks + 3) / 4;                 // blocks of 4 warps
+      auto env_int = [](const char* name, int dflt) {
+        const char* e = getenv(name);
+        return e ? atoi(e) : dflt;
+      };
+      DecryptFpParams f{};
+      f.ct = d_ct;
+      f.f0 = sk->fp0;
+      f.f1 = sk->fp1;
+      f.sched0 = sk->d_sched_p;
+      f.sched1 = sk->d_sched_q;
+      f.x = d_x;
+      f.count = count;
+      f.table_entries = p.table_entries;
+      f.debug_stage = want_fp ? env_int("IPCLB200_FP_DEBUG_STAGE", 0) : 0;
+      auto cap = [&](int per_sm) {
+        size_t c = (size_t)per_sm * sms;
+        return (int)(need < c ? need : c);
+      };
+      if (want_fp) {
+        int blocks = env_int("IPCLB200_FP_BLOCKS", 2);
+        if (blocks < 1 || blocks > 3) blocks = 2;
+        const int grid = cap(blocks);
+        TRY(table_ws_with_counter(s, (size_t)grid * 32 * FL * f.table_entries,
+                                  &f.table_ws, &f.work_counter, 1));
+        if (blocks == 3)
+          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3><<<grid, kBlockThreads, smem, s>>>(f);
+        else
+          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 2><<<grid, kBlockThreads, smem, s>>>(f);
+        g_ctx.launches++;
+      } else if (want_dual) {
+        DecryptDualParams d{};
+        const int grid = cap(3);
+        TRY(table_ws_with_counter(s, (size_t)grid * 32 * L * p.table_entries,
+                                  &p.table_ws, &p.work_counter));
+        uint32_t* fws = nullptr;
+        const size_t fwords = (size_t)grid * 32 * FL * f.table_entries;
+        TRY(table_ws_get((void*)((uintptr_t)s + 1), fwords + 1024, &fws));
+        f.table_ws = fws;
+        f.work_counter = p.work_counter;
+        d.i = p;
+        d.f = f;
+        d.sm_slots = fws + fwords;
+        d.fp_mask = (unsigned)env_int("IPCLB200_FP_MASK", 4);
+        d.slots_per_sm = 3;
+        CUDA_TRY(cudaMemsetAsync(d.sm_slots, 0, 1024 * sizeof(uint32_t), s));
+        decrypt_crt_dual_kernel<16, 4, kFpK, kFpT><<<grid, kBlockThreads, smem, s>>>(d);
+        g_ctx.launches++;
+      } else {
+        int ib = 2, fb = 1;
+        if (const char* e = getenv("IPCLB200_DUAL2")) sscanf(e, "%d,%d", &ib, &fb);
+        if (ib < 0 || ib > 3) ib = 2;
+        if (fb < 0 || fb > 2 || (ib == 0 && fb == 0)) fb = 1;
+        const int igrid = cap(ib ? ib : 1), fgrid = cap(fb ? fb : 1);
+        TRY(table_ws_with_counter(s, (size_t)igrid * 32 * L * p.table_entries,
+                                  &p.table_ws, &p.work_counter));
+        uint32_t* fws = nullptr;
+        TRY(table_ws_get((void*)((uintptr_t)s + 1),
+                         (size_t)fgrid * 32 * FL * f.table_entries, &fws));
+        f.table_ws = fws;
+        f.work_counter = p.work_counter;
+        // kernels with different shared-memory carve-outs cannot share an SM:
+        // ask for the same one for both
+        static bool carve_set = false;
+        if (!carve_set) {
+          const int carve = env_int("IPCLB200_CARVEOUT", 100);
+          if (carve >= 0) {
+            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_kernel<16, 4>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_fp224_kernel<kFpK, kFpT, kFpWords>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+          }
+          carve_set = true;
+        }
+        cudaStream_t s2 = g_ctx.aux_stream;
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(s2, g_ctx.ev_fork, 0));
+        if (ib) decrypt_crt_kernel<16, 4><<<igrid, kBlockThreads, 0, s>>>(p);
+        if (fb == 1)
+          decrypt_crt_fp224_kernel<kFpK, kFpT, kFpWords><<<fgrid, kBlockThreads, smem, s2>>>(f);
+        else if (fb == 2)
+          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3><<<fgrid, kBlockThreads, smem, s2>>>(f);
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_join, s2));
+        CUDA_TRY(cudaStreamWaitEvent(s, g_ctx.ev_join, 0));
+        g_ctx.launches += 2;
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      int grid = 0;
 #define F(K_, T_)                                                          \
   {                                                                        \
     TRY(grid_for(decrypt_crt_kernel<K_, T_>, 2 * count, T_, &grid));       \
@@ -786,8 +916,10 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
                               &p.table_ws, &p.work_counter));              \
     decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
   }
-    IPCLB200_DISPATCH(L, F)
+      IPCLB200_DISPATCH(L, F)
 #undef F
+      g_ctx.launches++;
+    }
     CrtFinishParams f{};
     f.x = d_x;
     f.p = sk->d_p;
@@ -804,7 +936,7 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     f.pt = d_pt;
     f.count = count;
     crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
-    g_ctx.launches += 2;
+    g_ctx.launches++;
     CUDA_TRY(cudaGetLastError());
   } else {
     const int L = sk->mnsq->L;
@@ -887,6 +1019,11 @@ void ipclb200_shutdown(void) {
   g_ctx.mod_cache.clear();
   if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
   g_ctx.stream = nullptr;
+  if (g_ctx.aux_stream) cudaStreamDestroy(g_ctx.aux_stream);
+  g_ctx.aux_stream = nullptr;
+  if (g_ctx.ev_fork) cudaEventDestroy(g_ctx.ev_fork);
+  if (g_ctx.ev_join) cudaEventDestroy(g_ctx.ev_join);
+  g_ctx.ev_fork = g_ctx.ev_join = nullptr;
   g_ctx.ready = false;
 }
 
@@ -1218,6 +1355,32 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
     hbn::to_words(hbn::sub(two256, inv), sk->ninv_q, 8);
   }
   sk->lambda_bits = hbn::bitlen(lam);
+  if (sk->L == kFpWords) {
+    // radix-2^22 constants of the FP64 role: n and R^3 mod n, R = 2^(22*96)
+    constexpr int FL = kFpLimbs;
+    std::vector<double> blk(4 * (size_t)FL);
+    Limbs Rf = hbn::pow2((unsigned)(kFpW * FL));
+    const Limbs* mods[2] = {&psq, &qsq};
+    for (int i = 0; i < 2; i++) {
+      const Limbs& m = *mods[i];
+      Limbs r1 = hbn::mod(Rf, m);
+      Limbs r3 = hbn::mod(hbn::mul(hbn::mod(hbn::mul(r1, r1), m), r1), m);
+      fp_limbs(m, blk.data() + (size_t)(2 * i) * FL, FL);
+      fp_limbs(r3, blk.data() + (size_t)(2 * i + 1) * FL, FL);
+    }
+    CUDA_TRY(cudaMalloc(&sk->d_fp, blk.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(sk->d_fp, blk.data(), blk.size() * sizeof(double),
+                        cudaMemcpyHostToDevice));
+    sk->fp0.n = sk->d_fp;
+    sk->fp0.r3 = sk->d_fp + FL;
+    sk->fp0.n32 = sk->mp2->mc.n;
+    sk->fp0.n0inv = hbn::neg_inv32(psq[0]) & kFpMask;
+    sk->fp1.n = sk->d_fp + 2 * FL;
+    sk->fp1.r3 = sk->d_fp + 3 * FL;
+    sk->fp1.n32 = sk->mq2->mc.n;
+    sk->fp1.n0inv = hbn::neg_inv32(qsq[0]) & kFpMask;
+    sk->fp_ok = true;
+  }
   *out = sk.release();
   return 0;
 }
@@ -1252,6 +1415,27 @@ int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct,
   TRY(upload_padded(d_ct, ct, CW, ctw, count, s));
   TRY(decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, s));
   CUDA_TRY(cudaMemcpyAsync(pt, d_pt, count * (size_t)(2 * pl) * 4,
+                           cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int ipclb200_crt_residues(const ipclb200_privkey* sk, const uint32_t* ct,
+                          size_t count, uint32_t* x, int* x_words) {
+  if (!sk || !ct || !x) return fail(IPCLB200_ERR_BAD_ARG, "crt_residues: null pointer");
+  if (x_words) *x_words = sk->L;
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int pl = sk->pl;
+  uint32_t *d_ct, *d_x, *d_pt;
+  TRY(scratch_get(0, count * (size_t)(2 * sk->L), &d_ct));
+  TRY(scratch_get(1, count * (size_t)(2 * sk->L), &d_x));
+  TRY(scratch_get(2, count * (size_t)(2 * pl), &d_pt));
+  TRY(upload_padded(d_ct, ct, 4 * pl, 2 * sk->L, count, s));
+  TRY(decrypt_dev_impl(sk, d_ct, count, 1, d_pt, d_x, s));
+  CUDA_TRY(cudaMemcpyAsync(x, d_x, count * (size_t)(2 * sk->L) * 4,
                            cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return 0;
@@ -1303,6 +1487,35 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_ctx.device);
     *sm_clock_mhz = khz / 1000.0;
   }
+  return 0;
+}
+
+int ipclb200_pipe_mix(int mode, double* ms_out) {
+  if (mode < 0 || mode > 4 || !ms_out)
+    return fail(IPCLB200_ERR_BAD_ARG, "pipe_mix: bad argument");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int threads = 256, blocks = g_ctx.sms * 4, iters = 4096;
+  uint32_t* d_out;
+  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(cudaEventRecord(a, s));
+    pipe_mix_kernel<<<blocks, threads, 0, s>>>(d_out, mode, iters, 3u + rep, 1.5);
+    CUDA_TRY(cudaEventRecord(b, s));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  g_ctx.launches += 4;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *ms_out = best;
   return 0;
 }
 

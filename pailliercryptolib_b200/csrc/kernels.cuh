@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "mont_core.cuh"
+#include "mont_fp64.cuh"
 #include "mont_tile.cuh"
 
 namespace ipclb200 {
@@ -483,14 +484,13 @@ struct DecryptCrtParams {
   unsigned int* work_counter;
 };
 
+// the integer-pipe role: claims chunks until the batch is exhausted
 template <int K, int T>
-__global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
-    decrypt_crt_kernel(const DecryptCrtParams p) {
+__device__ __forceinline__ void decrypt_int_role(const DecryptCrtParams& p,
+                                                 size_t gid) {
   using M = Mont<K, T>;
   constexpr int L = K * T;
   constexpr int GW = 32 / T;  // groups per warp
-  const size_t gpb = blockDim.x / T;
-  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
   uint32_t* tab = p.table_ws + gid * ((size_t)L * p.table_entries);
   const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
   for (;;) {
@@ -525,6 +525,250 @@ __global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
     modexp_sched_core<K, T>(acc, x, n, n0inv, side ? p.sched1 : p.sched0, tab);
     M::from_mont(x, acc, n, n0inv);
     if (valid) M::store(p.x + (inst * 2 + side) * L, x);
+  }
+}
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
+    decrypt_crt_kernel(const DecryptCrtParams p) {
+  const size_t gpb = blockDim.x / T;
+  decrypt_int_role<K, T>(p, blockIdx.x * gpb + threadIdx.x / T);
+}
+
+// --------------------------------------------------------------------------
+// K4f: the same CRT-decrypt modexp on the FP64 pipe (mont_fp64.cuh), and the
+// dual-pipe kernel that runs both roles side by side on every SM.
+//
+// The FP64 role takes the same chunks from the same work counter as the
+// integer role (8 ciphertexts of one side per warp: T = 4 lanes per integer in
+// both) and writes the same canonical 32-bit words to p.x, so crt_finish_kernel
+// does not know which pipe produced a residue.  Per chunk:
+//   stage the ciphertext words in shared memory, cut them into 22-bit limbs
+//   ct = lo + hi * R  ->  ct * R^-1 = mont(lo, 1) + hi  ->  * R^3  ->  ct * R
+//   odd powers x, x^3, ... into this group's table (int32 limbs, L2 resident)
+//   the host-built sliding-window schedule of p-1 (same bytes as the int role)
+//   leave Montgomery form (result <= n), exact carry propagation by one lane,
+//   repack to 32-bit words, n -> 0, store.
+// --------------------------------------------------------------------------
+constexpr int kFpStage = 136;  // staging words per group (128 + zero pad)
+
+struct DecryptFpParams {
+  const uint32_t* ct;  // count x 2*OW words
+  FpModConst f0, f1;   // p^2, q^2
+  const uint8_t *sched0, *sched1;
+  uint32_t* x;  // out: count x 2 x OW words
+  size_t count;
+  uint32_t* table_ws;  // int32 limbs: groups x table_entries x L
+  int table_entries;
+  unsigned int* work_counter;  // shared with the integer role
+  int debug_stage;  // 0 = off; k > 0: stop after stage k and emit the limbs
+};
+
+template <int K, int T, int OW>
+__device__ __forceinline__ void decrypt_fp_role(const DecryptFpParams& p,
+                                                size_t gid, double* bsm,
+                                                uint32_t* stg) {
+  using F = FpMont<K, T>;
+  constexpr int L = K * T;
+  constexpr int GW = 32 / T;
+  constexpr int WPL = OW / T;  // 32-bit words of a residue per lane
+  static_assert(2 * OW + 8 <= kFpStage, "staging too small");
+  static_assert(L + 4 <= kFpStage, "staging too small");
+  static_assert((2 * OW / T) % 4 == 0 && WPL % 4 == 0, "128-bit accesses");
+  const int t = F::lane_t();
+  uint32_t* tab = p.table_ws + gid * ((size_t)L * p.table_entries);
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= 2u * nchunks) break;
+    const int side = (int)(w & 1u);
+    const size_t inst = (size_t)(w >> 1) * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const double* gn = side ? p.f1.n : p.f0.n;
+    const double* gr3 = side ? p.f1.r3 : p.f0.r3;
+    const uint32_t* gn32 = side ? p.f1.n32 : p.f0.n32;
+    const uint32_t n0inv = side ? p.f1.n0inv : p.f0.n0inv;
+    const uint8_t* sched = side ? p.sched1 : p.sched0;
+    double n[K], a[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) n[j] = __ldg(gn + t * K + j);
+    // stage the 2*OW ciphertext words of this group, zero padded
+    {
+      const uint4* c4 =
+          reinterpret_cast<const uint4*>(p.ct + ii * (size_t)(2 * OW)) +
+          t * (2 * OW / T / 4);
+      uint4* s4 = reinterpret_cast<uint4*>(stg) + t * (2 * OW / T / 4);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2 * OW / T / 4; j++) s4[j] = c4[j];
+      if (t == 0) {
+        reinterpret_cast<uint4*>(stg)[2 * OW / 4] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(stg)[2 * OW / 4 + 1] = make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++)
+      a[j] = fp_from_u32(fp_limb_at(stg, kFpW * (t * K + j)));
+    do {
+      F::put_b_one(bsm);
+      F::mul(a, n, n0inv, bsm);  // lo * R^-1  (<= n)
+      if (p.debug_stage == 1) break;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int off = kFpW * (L + t * K + j);
+        const uint32_t h = (off < 64 * OW) ? fp_limb_at(stg, off) : 0u;
+        a[j] = __dadd_rn(a[j], fp_from_u32(h));
+      }
+      F::normalize(a);  // ct * R^-1 mod n, < 2n
+      if (p.debug_stage == 2) break;
+      F::put_b_global(bsm, gr3);
+      F::mul(a, n, n0inv, bsm);  // ct * R mod n: Montgomery form
+      if (p.debug_stage == 3) break;
+      // odd powers
+      const int nodd = sched[0];
+      F::store_tab(tab, a);
+      F::put_b(bsm, a);
+      F::mul(a, n, n0inv, bsm);  // x^2
+      if (p.debug_stage == 4) break;
+      F::put_b(bsm, a);
+      F::load_tab(a, tab);
+      for (int i = 1; i < nodd; i++) {
+        F::mul(a, n, n0inv, bsm);
+        F::store_tab(tab + (size_t)i * L, a);
+      }
+      if (p.debug_stage == 5) break;
+      F::load_tab(a, tab + (size_t)sched[1] * L);
+      F::put_b(bsm, a);
+      const uint8_t* op = sched + 2;
+#pragma unroll 1
+      for (uint32_t o = __ldg(op); o != 0xffu; o = __ldg(++op)) {
+        if (o) F::load_tab(a, tab + (size_t)(o - 1) * L);
+        F::mul(a, n, n0inv, bsm);
+        F::put_b(bsm, a);
+      }
+      if (p.debug_stage == 6) break;
+      F::put_b_one(bsm);
+      F::mul(a, n, n0inv, bsm);  // leave Montgomery form: <= n
+    } while (0);
+    // limbs -> exact 22-bit digits -> 32-bit words
+#pragma unroll
+    for (int j = 0; j < K; j++) stg[t * K + j] = fp_to_u32(a[j]);
+    if (t == 0) {
+      stg[L] = 0;
+      stg[L + 1] = 0;
+      stg[L + 2] = 0;
+    }
+    __syncwarp();
+    if (t == 0) {
+      uint32_t c = 0;
+      for (int g = 0; g < L; g++) {
+        const uint32_t v = stg[g] + c;
+        stg[g] = v & kFpMask;
+        c = v >> kFpW;
+      }
+    }
+    __syncwarp();
+    uint32_t wv[WPL];
+    bool eq = true;
+#pragma unroll
+    for (int j = 0; j < WPL; j++) {
+      const int k = t * WPL + j;
+      const int g0 = (32 * k) / kFpW;
+      const int o = 32 * k - kFpW * g0;
+      const uint64_t v = (uint64_t)stg[g0] | ((uint64_t)stg[g0 + 1] << kFpW) |
+                         ((uint64_t)stg[g0 + 2] << (2 * kFpW));
+      wv[j] = (uint32_t)(v >> o);
+      eq = eq && (wv[j] == __ldg(gn32 + k));
+    }
+    // the product is <= n; n itself (only for a ciphertext divisible by the
+    // prime) is the residue 0
+    {
+      const uint32_t be = __ballot_sync(IPCLB200_FULL_MASK, eq);
+      const uint32_t gm = ((1u << T) - 1u) << ((threadIdx.x & 31) & ~(T - 1));
+      if ((be & gm) == gm && p.debug_stage == 0) {
+#pragma unroll
+        for (int j = 0; j < WPL; j++) wv[j] = 0;
+      }
+    }
+    if (valid) {
+      uint4* d = reinterpret_cast<uint4*>(p.x + (inst * 2 + side) * OW) +
+                 t * (WPL / 4);
+#pragma unroll
+      for (int j = 0; j < WPL; j += 4)
+        d[j / 4] = make_uint4(wv[j], wv[j + 1], wv[j + 2], wv[j + 3]);
+    }
+  }
+}
+
+constexpr size_t fp_role_smem(int K, int T) {
+  return (size_t)(kBlockThreads / T) * (K * T + 1) * sizeof(double) +
+         (size_t)(kBlockThreads / T) * kFpStage * sizeof(uint32_t);
+}
+
+template <int K, int T, int OW>
+__device__ __forceinline__ void decrypt_fp_block(const DecryptFpParams& p) {
+  extern __shared__ double fp_smem[];
+  constexpr int gpb = kBlockThreads / T;
+  const int g = threadIdx.x / T;
+  uint32_t* stg0 =
+      reinterpret_cast<uint32_t*>(fp_smem + gpb * FpMont<K, T>::BSTRIDE);
+  decrypt_fp_role<K, T, OW>(p, (size_t)blockIdx.x * gpb + g,
+                            fp_smem + g * FpMont<K, T>::BSTRIDE,
+                            stg0 + g * kFpStage);
+}
+
+// FP64 role alone: MINB = 3 -> 168 registers, MINB <= 2 -> no register cap
+template <int K, int T, int OW, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB)
+    decrypt_crt_fp_kernel(const DecryptFpParams p) {
+  decrypt_fp_block<K, T, OW>(p);
+}
+
+// 224 registers: one block of this kernel fits next to two blocks of the
+// 144-register integer kernel on one SM (2*128*144 + 128*224 = 65536)
+template <int K, int T, int OW>
+__global__ void __maxnreg__(224)
+    decrypt_crt_fp224_kernel(const DecryptFpParams p) {
+  decrypt_fp_block<K, T, OW>(p);
+}
+
+// Both roles in one persistent kernel.  A block asks its SM for a slot number
+// (per-SM atomic counter) and bit `slot` of fp_mask decides its role, so every
+// SM hosts the same mix of integer-pipe and FP64-pipe warps, one warp of each
+// block per SM sub-partition.
+struct DecryptDualParams {
+  DecryptCrtParams i;
+  DecryptFpParams f;
+  unsigned int* sm_slots;  // zeroed before the launch, indexed by %smid
+  unsigned int fp_mask;
+  unsigned int slots_per_sm;
+};
+
+template <int K, int T, int FK, int FT>
+__global__ void __launch_bounds__(kBlockThreads, 3)
+    decrypt_crt_dual_kernel(const DecryptDualParams p) {
+  extern __shared__ double fp_smem[];
+  __shared__ unsigned int s_role;
+  if (threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int slot = atomicAdd(p.sm_slots + smid, 1u) % p.slots_per_sm;
+    s_role = (p.fp_mask >> slot) & 1u;
+  }
+  __syncthreads();
+  if (s_role) {
+    constexpr int gpb = kBlockThreads / FT;
+    const int g = threadIdx.x / FT;
+    uint32_t* stg0 =
+        reinterpret_cast<uint32_t*>(fp_smem + gpb * FpMont<FK, FT>::BSTRIDE);
+    decrypt_fp_role<FK, FT, K * T>(p.f, (size_t)blockIdx.x * gpb + g,
+                                   fp_smem + g * FpMont<FK, FT>::BSTRIDE,
+                                   stg0 + g * kFpStage);
+  } else {
+    const size_t gpb = kBlockThreads / T;
+    decrypt_int_role<K, T>(p.i, blockIdx.x * gpb + threadIdx.x / T);
   }
 }
 
@@ -863,6 +1107,68 @@ __global__ void int_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
   uint32_t s = 0;
 #pragma unroll
   for (int i = 0; i < 17; i++) s ^= e[i] ^ o[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+
+// --------------------------------------------------------------------------
+// Pipe-overlap probe: do IMAD.WIDE (integer multiply pipe) and DFMA (FP64
+// pipe) run at the same time on one SM sub-partition?  mode 0: every warp runs
+// IMAD.WIDE carry chains; 1: every warp runs independent DFMA chains; 2: warps
+// 0-3 / 8-11 / ... integer, warps 4-7 / 12-15 / ... DFMA (each sub-partition
+// hosts both kinds); 3: like 2 but the DFMA warps idle (half the integer work
+// alone); 4: like 2 but the integer warps idle.
+// --------------------------------------------------------------------------
+__global__ void pipe_mix_kernel(uint32_t* out, int mode, int iters, uint32_t a,
+                                double da) {
+  const int warp = threadIdx.x >> 5;
+  const bool fp_role = mode == 1 || (mode >= 2 && ((warp >> 2) & 1));
+  if ((mode == 3 && fp_role) || (mode == 4 && !fp_role)) return;
+  uint32_t s = 0;
+  if (!fp_role) {
+    uint32_t e[17], o[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) {
+      e[i] = threadIdx.x + i;
+      o[i] = threadIdx.x * 3 + i;
+    }
+    uint32_t x = a + threadIdx.x, y = 5u;
+    for (int it = 0; it < iters; it++) {
+      mad_lo_cc(e[0], x, y, e[0]);
+      madc_hi_cc(e[1], x, y, e[1]);
+#pragma unroll
+      for (int i = 2; i < 16; i += 2) {
+        madc_lo_cc(e[i], x, y, e[i]);
+        madc_hi_cc(e[i + 1], x, y, e[i + 1]);
+      }
+      addc(e[16], e[16], 0);
+      mad_lo_cc(o[0], y, x, o[0]);
+      madc_hi_cc(o[1], y, x, o[1]);
+#pragma unroll
+      for (int i = 2; i < 16; i += 2) {
+        madc_lo_cc(o[i], y, x, o[i]);
+        madc_hi_cc(o[i + 1], y, x, o[i + 1]);
+      }
+      addc(o[16], o[16], 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 17; i++) s ^= e[i] ^ o[i];
+  } else {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = (double)(threadIdx.x + i);
+    const double x = da + (double)threadIdx.x, y = 3.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = __fma_rn(x, y, acc[i]);
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = __fma_rn(y, x, acc[i]);
+    }
+    double t = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) t += acc[i];
+    s = (uint32_t)__double2loint(t) ^ (uint32_t)__double2hiint(t);
+  }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

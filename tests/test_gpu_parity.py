@@ -273,6 +273,52 @@ def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     assert np.array_equal(alt, pt)
 
 
+FP_CONFIGS = [
+    ("int", {}),
+    ("fp", {"IPCLB200_FP_BLOCKS": "2"}),
+    ("fp", {"IPCLB200_FP_BLOCKS": "3"}),
+    ("dual", {"IPCLB200_FP_MASK": "4"}),
+    ("dual", {"IPCLB200_FP_MASK": "6"}),
+    ("dual2", {"IPCLB200_DUAL2": "2,1"}),
+    ("dual2", {"IPCLB200_DUAL2": "1,2"}),
+]
+
+
+@pytest.mark.parametrize("mode,env", FP_CONFIGS,
+                         ids=["-".join([m] + list(e.values())) for m, e in FP_CONFIGS])
+def test_decrypt_pipes_residues_vs_pow(capi, keys, mode, env, monkeypatch):
+    """every pipe configuration of the CRT-decrypt modexp (integer pipe, FP64
+    pipe, both in one kernel, both as two kernels sharing the work counter)
+    leaves the canonical residues ct^(p-1) mod p^2, ct^(q-1) mod q^2 -- checked
+    against Python pow() -- and the same plaintexts; includes ciphertexts 0, 1,
+    n^2-1 and multiples of p and q^2 (residue 0 / the modulus itself)"""
+    k = keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    nsq = n * n
+    rng = np.random.default_rng(2200)
+    count = 203
+    cts = [int.from_bytes(rng.bytes(512), "little") % nsq for _ in range(count)]
+    cts[:5] = [0, 1, nsq - 1, p * 12345, q * q * 3 % nsq]
+    ct = batch_to_limbs(cts, 128)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    monkeypatch.setenv("IPCLB200_DECRYPT", "int")
+    base = sk.decrypt(ct)
+    monkeypatch.setenv("IPCLB200_DECRYPT", mode)
+    for a, b in env.items():
+        monkeypatch.setenv(a, b)
+    x = sk.crt_residues(ct)
+    assert x.shape == (count, 2, 64)
+    got = [[from_limbs(x[i, s]) for s in (0, 1)] for i in range(count)]
+    want = [[pow(c, p - 1, p * p), pow(c, q - 1, q * q)] for c in cts]
+    assert got == want
+    assert np.array_equal(sk.decrypt(ct), base)
+    # a real round trip on top
+    pk = capi.PubKey(to_limbs(n, 64), to_limbs(k["hs"], 128), 1024)
+    pt = random_limbs(rng, 77, 64, top_mask=0x3FFFFFFF)
+    assert np.array_equal(sk.decrypt(pk.encrypt(pt, random_limbs(rng, 77, 32))), pt)
+
+
 def test_concurrent_callers_through_cabi(capi, keys):
     """the C ABI is re-entrant: four host threads encrypt and decrypt on the
     same key objects at once (the reference calls encrypt/decrypt concurrently
