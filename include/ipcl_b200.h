@@ -147,6 +147,32 @@ int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
                          size_t count, int use_crt, uint32_t* d_pt,
                          void* stream);
 
+/* ---- device-resident batches ------------------------------------------------
+ * Lets a host keep ciphertext batches in HBM between encrypt -> + -> * ->
+ * decrypt instead of round-tripping through vector<BigNumber> (the copies at
+ * ipcl/base_text.cpp:102 and ipcl/mod_exp.cpp:627-632); the ipcl:: layer uses
+ * these for its device-resident CipherText.  The counterpart in the reference
+ * is the buffer acquire/release of the QAT offload
+ * (module/heqat/heqat/include/heqat/bnops.h:121-148).
+ * All of them work on the library's own stream, ipclb200_stream(), which is
+ * also the stream to hand to the *_dev entry points for work on these buffers:
+ * allocation, copies, kernels and frees are then ordered on that one stream.
+ *   dev_alloc / dev_free : stream-ordered (cudaMallocAsync / cudaFreeAsync)
+ *   dev_upload           : the host buffer may be reused on return
+ *   dev_download         : waits until the data has arrived
+ *   dev_copy             : device to device, `bytes` bytes
+ *   class_words          : the kernel size class (16,32,48,64,96,128,192,256)
+ *                          that holds `words` words, 0 if none; the *_dev
+ *                          entry points need strides that are a size class */
+void* ipclb200_stream(void);
+int ipclb200_dev_alloc(size_t bytes, void** d_out);
+int ipclb200_dev_free(void* d);
+int ipclb200_dev_upload(void* d, const void* h, size_t bytes);
+int ipclb200_dev_download(void* h, const void* d, size_t bytes);
+int ipclb200_dev_copy(void* d_dst, const void* d_src, size_t bytes);
+int ipclb200_sync(void);
+int ipclb200_class_words(int words);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs the integer-pipe microbenchmark (dependent-carry IMAD.WIDE.U32 chains on
  * every SM) and returns the measured 32x32->64 multiply-accumulate rate; this

@@ -117,7 +117,7 @@ def build_cpp_tests(force=False):
     os.makedirs(os.path.dirname(CPP_TEST_BIN), exist_ok=True)
     srcs = [os.path.join(CPP_TEST_DIR, f) for f in
             ("main.cpp", "test_cryptography.cpp", "test_ops.cpp",
-             "test_serialization.cpp")]
+             "test_serialization.cpp", "test_device_resident.cpp")]
     deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"),
                    os.path.join(CPP_TEST_DIR, "iso_vectors.hpp"), IPCL_LIB]
     if force or not _newer(CPP_TEST_BIN, deps):

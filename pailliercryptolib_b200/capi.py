@@ -32,7 +32,9 @@ EXPORTS = [
     "ipclb200_encrypt_dev", "ipclb200_privkey_create",
     "ipclb200_privkey_destroy", "ipclb200_decrypt", "ipclb200_decrypt_dev",
     "ipclb200_int_peak", "ipclb200_launch_count", "ipclb200_crt_residues",
-    "ipclb200_pipe_mix",
+    "ipclb200_pipe_mix", "ipclb200_stream", "ipclb200_dev_alloc",
+    "ipclb200_dev_free", "ipclb200_dev_upload", "ipclb200_dev_download",
+    "ipclb200_dev_copy", "ipclb200_sync", "ipclb200_class_words",
 ]
 
 

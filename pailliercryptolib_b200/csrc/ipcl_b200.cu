@@ -261,6 +261,16 @@ int ensure_init_locked() {
   CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.aux_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
+  {
+    // device-resident batches come from the stream-ordered pool: keep freed
+    // blocks cached instead of returning them to the OS at every synchronise
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~(uint64_t)0;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   g_ctx.device = dev;
   g_ctx.sms = prop.multiProcessorCount;
   g_ctx.ready = true;
@@ -1455,6 +1465,71 @@ int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
   TRY(scratch_get(6, count * (size_t)(4 * pl), &d_x));
   return decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, (cudaStream_t)stream);
 }
+
+// ---- device-resident batches ------------------------------------------------
+void* ipclb200_stream(void) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (ensure_init_locked() != 0) return nullptr;
+  return (void*)g_ctx.stream;
+}
+
+int ipclb200_dev_alloc(size_t bytes, void** d_out) {
+  if (!d_out) return fail(IPCLB200_ERR_BAD_ARG, "dev_alloc: null pointer");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  CUDA_TRY(cudaMallocAsync(d_out, bytes ? bytes : 4, g_ctx.stream));
+  return 0;
+}
+
+int ipclb200_dev_free(void* d) {
+  if (!d) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (!g_ctx.ready) return 0;  // the context (and its pool) is already gone
+  CUDA_TRY(cudaSetDevice(g_ctx.device));
+  CUDA_TRY(cudaFreeAsync(d, g_ctx.stream));
+  return 0;
+}
+
+int ipclb200_dev_upload(void* d, const void* h, size_t bytes) {
+  if (!d || !h) return fail(IPCLB200_ERR_BAD_ARG, "dev_upload: null pointer");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  // pageable source: the call returns once the data is staged, so the caller
+  // may reuse h; pinned source: wait for the copy
+  CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, h) == cudaSuccess &&
+      at.type == cudaMemoryTypeHost)
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  cudaGetLastError();
+  return 0;
+}
+
+int ipclb200_dev_download(void* h, const void* d, size_t bytes) {
+  if (!d || !h) return fail(IPCLB200_ERR_BAD_ARG, "dev_download: null pointer");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  return 0;
+}
+
+int ipclb200_dev_copy(void* d_dst, const void* d_src, size_t bytes) {
+  if (!d_dst || !d_src) return fail(IPCLB200_ERR_BAD_ARG, "dev_copy: null pointer");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+  return 0;
+}
+
+int ipclb200_sync(void) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  return 0;
+}
+
+int ipclb200_class_words(int words) { return words > 0 ? class_words(words) : 0; }
 
 // ---- measurement ----------------------------------------------------------
 int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {

@@ -6,6 +6,8 @@
 //   ct + ct   batched modular multiply            (ipclb200_modmul)
 //   ct + pt   encode pt without obfuscator, then ct + ct
 //   ct * pt   batched modexp with the shared modulus n^2   (ipclb200_modexp)
+// and operands and results stay in HBM (device-resident texts, base_text.hpp):
+// encrypt -> + -> * -> decrypt is four kernel launches and no marshalling.
 #ifndef IPCL_B200_CIPHERTEXT_HPP_
 #define IPCL_B200_CIPHERTEXT_HPP_
 
@@ -31,6 +33,9 @@ class CipherText : public BaseText {
   // Takes ownership of a freshly unmarshalled batch (addition to the
   // reference interface: avoids copying 64 Ki BigNumbers a second time).
   CipherText(const PublicKey& pk, std::vector<BigNumber>&& bn_vec);
+  // back-end internal: a batch that lives in HBM (PublicKey::encrypt and the
+  // operators below); the BigNumbers are built on first access
+  CipherText(const PublicKey& pk, std::shared_ptr<detail::DeviceBatch> dev);
 
   CipherText(const CipherText& ct);
   CipherText& operator=(const CipherText& other);

@@ -20,6 +20,8 @@ class PlainText : public BaseText {
   explicit PlainText(const BigNumber& bn);
   explicit PlainText(const std::vector<BigNumber>& bn_v);
   explicit PlainText(std::vector<BigNumber>&& bn_v);
+  // back-end internal: a batch that lives in HBM (PrivateKey::decrypt)
+  explicit PlainText(std::shared_ptr<detail::DeviceBatch> dev);
   PlainText(const PlainText& pt);
   PlainText& operator=(const PlainText& other);
 

@@ -5,8 +5,11 @@
 #include "ipcl/base_text.hpp"
 
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 #include <utility>
 
+#include "device_batch.hpp"
 #include "ipcl/utils/util.hpp"
 #include "text_util.hpp"
 
@@ -27,7 +30,55 @@ std::vector<BigNumber> rotated(const std::vector<BigNumber>& v, int shift) {
   return out;
 }
 
+bool deviceResidentEnabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("IPCL_B200_DEVICE_RESIDENT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace detail
+
+// lazy host materialisation happens inside const accessors that several
+// threads may call on one text; one process-wide lock is enough (it is taken
+// once per text)
+static std::mutex g_materialize_mutex;
+
+BaseText::BaseText(std::shared_ptr<detail::DeviceBatch> dev)
+    : m_size(dev->count), m_dev(std::move(dev)), m_host_valid(false) {}
+
+void BaseText::ensureHost() const {
+  if (m_host_valid.load(std::memory_order_acquire)) return;
+  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  if (m_host_valid.load(std::memory_order_relaxed)) return;
+  m_texts = m_dev->toHost();
+  m_host_valid.store(true, std::memory_order_release);
+}
+
+void BaseText::hostOnly() {
+  ensureHost();
+  m_dev.reset();
+}
+
+std::shared_ptr<detail::DeviceBatch> BaseText::deviceBatch(int words) const {
+  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  if (m_dev && m_dev->words == words) return m_dev;
+  if (!m_host_valid.load()) {
+    // resident at another width: go through the host form
+    m_texts = m_dev->toHost();
+    m_host_valid.store(true);
+  }
+  if (!detail::DeviceBatch::fits(m_texts, words)) return nullptr;
+  auto b = detail::DeviceBatch::fromHost(m_texts, words);
+  if (!m_dev) m_dev = b;  // keep it for the next operator on this text
+  return b;
+}
+
+const std::vector<BigNumber>& BaseText::texts() const {
+  ensureHost();
+  return m_texts;
+}
 
 #define TEXT_INDEX_CHECK(i, what) \
   ERROR_CHECK((i) < m_size, "BaseText: " what " index is out of range")
@@ -48,28 +99,46 @@ BaseText::BaseText(const std::vector<BigNumber>& bn_v)
 BaseText::BaseText(std::vector<BigNumber>&& bn_v)
     : m_texts(std::move(bn_v)), m_size(m_texts.size()) {}
 
-BaseText::BaseText(const BaseText& bt) : m_texts(bt.m_texts), m_size(bt.m_size) {}
+// a copy shares the (immutable) device batch and copies the host form only if
+// it exists
+BaseText::BaseText(const BaseText& bt) : m_size(bt.m_size) {
+  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  m_dev = bt.m_dev;
+  const bool valid = bt.m_host_valid.load();
+  if (valid) m_texts = bt.m_texts;
+  m_host_valid.store(valid);
+}
 
 BaseText& BaseText::operator=(const BaseText& other) {
   if (this != &other) {
-    m_texts = other.m_texts;
+    std::lock_guard<std::mutex> lk(g_materialize_mutex);
     m_size = other.m_size;
+    m_dev = other.m_dev;
+    const bool valid = other.m_host_valid.load();
+    if (valid)
+      m_texts = other.m_texts;
+    else
+      m_texts.clear();
+    m_host_valid.store(valid);
   }
   return *this;
 }
 
 BigNumber& BaseText::operator[](const std::size_t idx) {
   ERROR_CHECK(idx < m_size, "BaseText:operator[] index is out of range");
+  hostOnly();  // the caller may write through the reference
   return m_texts[idx];
 }
 
 BigNumber BaseText::getElement(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElement");
+  ensureHost();
   return m_texts[idx];
 }
 
 std::vector<uint32_t> BaseText::getElementVec(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElementVec");
+  ensureHost();
   std::vector<uint32_t> words;
   m_texts[idx].num2vec(words);
   return words;
@@ -77,6 +146,7 @@ std::vector<uint32_t> BaseText::getElementVec(const std::size_t& idx) const {
 
 std::string BaseText::getElementHex(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElementHex");
+  ensureHost();
   std::string hex;
   m_texts[idx].num2hex(hex);
   return hex;
@@ -85,29 +155,37 @@ std::string BaseText::getElementHex(const std::size_t& idx) const {
 std::vector<BigNumber> BaseText::getChunk(const std::size_t& start,
                                           const std::size_t& size) const {
   ERROR_CHECK(start + size <= m_size, "BaseText: getChunk parameter is incorrect");
+  ensureHost();
   return {m_texts.begin() + static_cast<std::ptrdiff_t>(start),
           m_texts.begin() + static_cast<std::ptrdiff_t>(start + size)};
 }
 
 void BaseText::insert(const std::size_t pos, BigNumber& bn) {
   ERROR_CHECK(pos <= m_size, "BaseText: insert position is out of range");
+  hostOnly();
   m_texts.insert(m_texts.begin() + static_cast<std::ptrdiff_t>(pos), bn);
   m_size = m_texts.size();
 }
 
 void BaseText::remove(const std::size_t pos, const std::size_t length) {
   ERROR_CHECK(pos + length < m_size, "BaseText: remove position is out of range");
+  hostOnly();
   const auto first = m_texts.begin() + static_cast<std::ptrdiff_t>(pos);
   m_texts.erase(first, first + static_cast<std::ptrdiff_t>(length));
   m_size = m_texts.size();
 }
 
 void BaseText::clear() {
+  m_dev.reset();
   m_texts.clear();
+  m_host_valid.store(true);
   m_size = 0;
 }
 
-std::vector<BigNumber> BaseText::getTexts() const { return m_texts; }
+std::vector<BigNumber> BaseText::getTexts() const {
+  ensureHost();
+  return m_texts;
+}
 
 std::size_t BaseText::getSize() const { return m_size; }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <utility>
 
+#include "device_batch.hpp"
 #include "ipcl/mod_exp.hpp"
 #include "text_util.hpp"
 
@@ -25,6 +26,10 @@ CipherText::CipherText(const PublicKey& pk, const std::vector<BigNumber>& bn_v)
 CipherText::CipherText(const PublicKey& pk, std::vector<BigNumber>&& bn_v)
     : BaseText(std::move(bn_v)), m_pk(std::make_shared<PublicKey>(pk)) {}
 
+CipherText::CipherText(const PublicKey& pk,
+                       std::shared_ptr<detail::DeviceBatch> dev)
+    : BaseText(std::move(dev)), m_pk(std::make_shared<PublicKey>(pk)) {}
+
 CipherText::CipherText(const CipherText& ct) : BaseText(ct), m_pk(ct.m_pk) {}
 
 CipherText& CipherText::operator=(const CipherText& other) {
@@ -41,8 +46,23 @@ CipherText CipherText::operator+(const CipherText& other) const {
   ERROR_CHECK(*(m_pk->getN()) == *(other.m_pk->getN()),
               "CT + CT error: 2 different public keys detected!");
   if (m_size == 1)
-    return CipherText(*m_pk, raw_add(m_texts.front(), other.m_texts.front()));
-  return CipherText(*m_pk, modMul(m_texts, other.m_texts, *(m_pk->getNSQ())));
+    return CipherText(*m_pk, raw_add(texts().front(), other.texts().front()));
+  // device-resident: one ipclb200_modmul_dev on the batches where they are
+  const int W = 2 * static_cast<int>(m_pk->getN()->words().size());
+  if (detail::deviceResidentEnabled() && detail::isClassWords(W)) {
+    auto a = deviceBatch(W);
+    auto b = a ? other.deviceBatch(W) : nullptr;
+    if (a && b) {
+      std::vector<uint32_t> mod(static_cast<std::size_t>(W));
+      m_pk->getNSQ()->toWords(mod.data(), mod.size());
+      auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
+      DEVICE_CHECK(ipclb200_modmul_dev(a->ptr(), b->ptr(), mod.data(), W, m_size,
+                                       b_size == 1 ? IPCLB200_SHARED_B : 0u,
+                                       out->ptr(), ipclb200_stream()));
+      return CipherText(*m_pk, std::move(out));
+    }
+  }
+  return CipherText(*m_pk, modMul(texts(), other.texts(), *(m_pk->getNSQ())));
 }
 
 // ct + pt: encode pt without obfuscation, then ct + ct (:75-80)
@@ -57,23 +77,48 @@ CipherText CipherText::operator*(const PlainText& other) const {
   ERROR_CHECK(this->m_size == b_size || b_size == 1,
               "CT * PT error: Size mismatch!");
   if (m_size == 1)
-    return CipherText(*m_pk, raw_mul(m_texts.front(), other.texts().front()));
+    return CipherText(*m_pk, raw_mul(texts().front(), other.texts().front()));
+  // device-resident: one ipclb200_modexp_dev, base = the ciphertexts where they
+  // are, exponent = the plaintexts (uploaded once if they are host values)
+  const int W = 2 * static_cast<int>(m_pk->getN()->words().size());
+  if (detail::deviceResidentEnabled() && detail::isClassWords(W)) {
+    int ew = 0, ebits = 0;
+    if (other.isHostMaterialized()) {
+      ew = detail::maxWords(other.texts());
+      for (const auto& x : other.texts()) ebits = std::max(ebits, x.BitSize());
+    } else {
+      ew = W / 2;  // came out of decrypt: n-word values
+      ebits = 32 * ew;
+    }
+    auto a = deviceBatch(W);
+    auto e = a ? other.deviceBatch(ew) : nullptr;
+    if (a && e) {
+      std::vector<uint32_t> mod(static_cast<std::size_t>(W));
+      m_pk->getNSQ()->toWords(mod.data(), mod.size());
+      auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
+      DEVICE_CHECK(ipclb200_modexp_dev(
+          a->ptr(), e->ptr(), mod.data(), W, ew, ebits > 0 ? ebits : 1, m_size,
+          IPCLB200_SHARED_MOD | (b_size == 1 ? IPCLB200_SHARED_EXP : 0u),
+          out->ptr(), ipclb200_stream()));
+      return CipherText(*m_pk, std::move(out));
+    }
+  }
   if (b_size == 1) {
     std::vector<BigNumber> b_v(m_size, other.texts().front());
-    return CipherText(*m_pk, raw_mul(m_texts, b_v));
+    return CipherText(*m_pk, raw_mul(texts(), b_v));
   }
-  return CipherText(*m_pk, raw_mul(m_texts, other.texts()));
+  return CipherText(*m_pk, raw_mul(texts(), other.texts()));
 }
 
 CipherText CipherText::getCipherText(const size_t& idx) const {
   ERROR_CHECK(idx < m_size, "CipherText::getCipherText index is out of range");
-  return CipherText(*m_pk, m_texts[idx]);
+  return CipherText(*m_pk, texts()[idx]);
 }
 
 std::shared_ptr<PublicKey> CipherText::getPubKey() const { return m_pk; }
 
 CipherText CipherText::rotate(int shift) const {
-  return CipherText(*m_pk, detail::rotated(m_texts, shift));
+  return CipherText(*m_pk, detail::rotated(texts(), shift));
 }
 
 BigNumber CipherText::raw_add(const BigNumber& a, const BigNumber& b) const {

@@ -17,6 +17,8 @@ PlainText::PlainText(const std::vector<uint32_t>& n_v) : BaseText(n_v) {}
 PlainText::PlainText(const BigNumber& bn) : BaseText(bn) {}
 PlainText::PlainText(const std::vector<BigNumber>& bn_v) : BaseText(bn_v) {}
 PlainText::PlainText(std::vector<BigNumber>&& bn_v) : BaseText(std::move(bn_v)) {}
+PlainText::PlainText(std::shared_ptr<detail::DeviceBatch> dev)
+    : BaseText(std::move(dev)) {}
 PlainText::PlainText(const PlainText& pt) : BaseText(pt) {}
 
 PlainText& PlainText::operator=(const PlainText& other) {
@@ -36,16 +38,16 @@ PlainText::operator std::vector<uint32_t>() const {
 
 PlainText::operator BigNumber() const {
   ERROR_CHECK(m_size > 0, "PlainText: type conversion to BigNumber error");
-  return m_texts.front();
+  return texts().front();
 }
 
 PlainText::operator std::vector<BigNumber>() const {
   ERROR_CHECK(m_size > 0, "PlainText: type conversion to BigNumber vector error");
-  return m_texts;
+  return texts();
 }
 
 PlainText PlainText::rotate(int shift) const {
-  return PlainText(detail::rotated(m_texts, shift));
+  return PlainText(detail::rotated(texts(), shift));
 }
 
 }  // namespace ipcl

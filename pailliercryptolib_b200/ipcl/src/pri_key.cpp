@@ -7,6 +7,7 @@
 // ipclb200_decrypt call.
 #include "ipcl/pri_key.hpp"
 
+#include "device_batch.hpp"
 #include "ipcl/utils/util.hpp"
 #include "ipcl_b200.h"
 #include "marshal.hpp"
@@ -70,6 +71,20 @@ PlainText PrivateKey::decrypt(const CipherText& ct) const {
               "decrypt: The value of N in public key mismatch.");
   const std::size_t ct_size = ct.getSize();
   ERROR_CHECK(ct_size > 0, "decrypt: Cannot decrypt empty CipherText");
+
+  // device-resident: the ciphertexts are (or are put) in HBM, the plaintexts
+  // stay there until somebody reads them
+  const int pl = static_cast<int>(m_q->words().size());
+  if (detail::deviceResidentEnabled() && detail::isClassWords(2 * pl) &&
+      detail::isClassWords(4 * pl)) {
+    if (auto d_ct = ct.deviceBatch(4 * pl)) {
+      auto d_pt = std::make_shared<detail::DeviceBatch>(ct_size, 2 * pl);
+      DEVICE_CHECK(ipclb200_decrypt_dev(m_dev->h, d_ct->ptr(), ct_size,
+                                        m_enable_crt ? 1 : 0, d_pt->ptr(),
+                                        ipclb200_stream()));
+      return PlainText(std::move(d_pt));
+    }
+  }
 
   std::vector<BigNumber> pt_bn(ct_size);
   if (m_enable_crt)

@@ -9,6 +9,7 @@
 
 #include <mutex>
 
+#include "device_batch.hpp"
 #include "ipcl/ciphertext.hpp"
 #include "ipcl/mod_exp.hpp"
 #include "ipcl/utils/util.hpp"
@@ -159,29 +160,15 @@ void PublicKey::applyObfuscator(std::vector<BigNumber>& ciphertext) const {
   ciphertext = modMul(ciphertext, obf, *m_nsquare);
 }
 
-std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
-                                              bool make_secure) const {
-  const std::size_t sz = pt.size();
+// the randoms of one batch as a flat r_words-strided limb buffer
+// (pub_key.cpp:51-80: getRandomBN(m_randbits) per element for DJN, a value in
+// [1, n-1] otherwise; setRandom() injects fixed ones, :92-95)
+void PublicKey::flatRandoms(std::size_t sz, std::vector<uint32_t>& f_r,
+                            int& r_words) const {
   const int nl = static_cast<int>(m_n->words().size());
-  ipclb200_pubkey* dev = deviceKey();
-
-  // (n*pt + 1) mod n^2 only depends on pt mod n; bring negative or oversize
-  // plaintexts into [0, n) so they fit the n-word slot
-  const std::vector<BigNumber>* pp = &pt;
-  std::vector<BigNumber> reduced;
-  for (std::size_t i = 0; i < sz; i++) {
-    if (pt[i].isNegative() || static_cast<int>(pt[i].words().size()) > nl) {
-      if (reduced.empty()) reduced = pt;
-      reduced[i] = pt[i] % (*m_n);
-      pp = &reduced;
-    }
-  }
-  std::vector<uint32_t> f_pt, f_r, f_ct(sz * 2 * static_cast<std::size_t>(nl));
-  detail::pack(*pp, nl, f_pt);
-  int r_words = 0;
-  if (make_secure && m_enable_DJN && !m_testv) {
-    // fresh DJN randoms (pub_key.cpp:59-61: getRandomBN(m_randbits) each):
-    // drawn straight into the flat buffer with one entropy call for the batch
+  if (m_enable_DJN && !m_testv) {
+    // fresh DJN randoms drawn straight into the flat buffer with one entropy
+    // call for the batch
     r_words = (m_randbits + 31) / 32;
     f_r.resize(sz * static_cast<std::size_t>(r_words));
     rand32u(f_r);
@@ -190,15 +177,44 @@ std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
       for (std::size_t i = 0; i < sz; i++)
         f_r[i * static_cast<std::size_t>(r_words) + r_words - 1] &= mask;
     }
-  } else if (make_secure) {
-    std::vector<BigNumber> r = drawRandoms(sz);
-    for (auto& x : r) {
-      ERROR_CHECK(!x.isNegative(), "encrypt: negative random");
-      if (static_cast<int>(x.words().size()) > 2 * nl) x = x % (*m_nsquare);
-    }
-    r_words = detail::maxWords(r);
-    detail::pack(r, r_words, f_r);
+    return;
   }
+  std::vector<BigNumber> r = drawRandoms(sz);
+  for (auto& x : r) {
+    ERROR_CHECK(!x.isNegative(), "encrypt: negative random");
+    if (static_cast<int>(x.words().size()) > 2 * nl) x = x % (*m_nsquare);
+  }
+  r_words = detail::maxWords(r);
+  detail::pack(r, r_words, f_r);
+}
+
+// (n*pt + 1) mod n^2 only depends on pt mod n: negative or oversize plaintexts
+// are brought into [0, n) so they fit the n-word slot
+static const std::vector<BigNumber>& reducedPlain(
+    const std::vector<BigNumber>& pt, const BigNumber& n, int nl,
+    std::vector<BigNumber>& reduced) {
+  const std::vector<BigNumber>* pp = &pt;
+  for (std::size_t i = 0; i < pt.size(); i++) {
+    if (pt[i].isNegative() || static_cast<int>(pt[i].words().size()) > nl) {
+      if (reduced.empty()) reduced = pt;
+      reduced[i] = pt[i] % n;
+      pp = &reduced;
+    }
+  }
+  return *pp;
+}
+
+std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
+                                              bool make_secure) const {
+  const std::size_t sz = pt.size();
+  const int nl = static_cast<int>(m_n->words().size());
+  ipclb200_pubkey* dev = deviceKey();
+  std::vector<BigNumber> reduced;
+  const std::vector<BigNumber>& pp = reducedPlain(pt, *m_n, nl, reduced);
+  std::vector<uint32_t> f_pt, f_r, f_ct(sz * 2 * static_cast<std::size_t>(nl));
+  detail::pack(pp, nl, f_pt);
+  int r_words = 0;
+  if (make_secure) flatRandoms(sz, f_r, r_words);
   DEVICE_CHECK(ipclb200_encrypt(dev, f_pt.data(), nl,
                                 make_secure ? f_r.data() : nullptr, r_words, sz,
                                 make_secure ? 1 : 0, f_ct.data()));
@@ -209,6 +225,36 @@ CipherText PublicKey::encrypt(const PlainText& pt, bool make_secure) const {
   ERROR_CHECK(m_isInitialized, "encrypt: Public key is NOT initialized.");
   const std::size_t pt_size = pt.getSize();
   ERROR_CHECK(pt_size > 0, "encrypt: Cannot encrypt empty PlainText");
+  const int nl = static_cast<int>(m_n->words().size());
+  if (detail::deviceResidentEnabled() && detail::isClassWords(2 * nl)) {
+    // device-resident: plaintexts and randoms go up once, the ciphertexts stay
+    // in HBM until somebody reads them
+    std::shared_ptr<detail::DeviceBatch> d_pt;
+    if (!pt.isHostMaterialized()) {
+      d_pt = pt.deviceBatch(nl);
+    } else {
+      std::vector<BigNumber> reduced;
+      d_pt = detail::DeviceBatch::fromHost(
+          reducedPlain(pt.texts(), *m_n, nl, reduced), nl);
+    }
+    if (d_pt) {
+      ipclb200_pubkey* dev = deviceKey();
+      std::shared_ptr<detail::DeviceBatch> d_r;
+      int r_words = 0;
+      if (make_secure) {
+        std::vector<uint32_t> f_r;
+        flatRandoms(pt_size, f_r, r_words);
+        d_r = std::make_shared<detail::DeviceBatch>(pt_size, r_words);
+        DEVICE_CHECK(ipclb200_dev_upload(d_r->d, f_r.data(), d_r->bytes()));
+      }
+      auto d_ct = std::make_shared<detail::DeviceBatch>(pt_size, 2 * nl);
+      DEVICE_CHECK(ipclb200_encrypt_dev(dev, d_pt->ptr(), nl,
+                                        make_secure ? d_r->ptr() : nullptr,
+                                        r_words, pt_size, make_secure ? 1 : 0,
+                                        d_ct->ptr(), ipclb200_stream()));
+      return CipherText(*this, std::move(d_ct));
+    }
+  }
   return CipherText(*this, raw_encrypt(pt.texts(), make_secure));
 }
 

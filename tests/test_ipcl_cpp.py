@@ -17,7 +17,8 @@ def binary():
     return build.CPP_TEST_BIN
 
 
-@pytest.mark.parametrize("suite", ["CryptoTest", "OperationTest", "SerialTest"])
+@pytest.mark.parametrize("suite", ["CryptoTest", "OperationTest", "SerialTest",
+                                   "DeviceResidentTest"])
 def test_cpp_suite(binary, suite):
     env = dict(os.environ, OMP_NUM_THREADS="4")
     r = subprocess.run([binary, suite], stdout=subprocess.PIPE,
