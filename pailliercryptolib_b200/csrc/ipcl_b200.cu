@@ -218,7 +218,7 @@ struct Ctx {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // grow-only scratch buffers for the host-pointer entry points
-  static const int kSlots = 8;
+  static const int kSlots = 10;
   uint32_t* scratch[kSlots] = {};
   size_t scratch_words[kSlots] = {};
   // window-table workspace per stream
@@ -424,7 +424,8 @@ int download_padded(uint32_t* h, const uint32_t* d, int words, int L,
 // launch helpers (device pointers, any stream)
 // ---------------------------------------------------------------------------
 int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
-  p.window = pick_window(p.exp_bits);
+  // a schedule needs 2^(kSchedWindow-1) table entries per group
+  p.window = p.sched ? kSchedWindow - 1 : pick_window(p.exp_bits);
   const int T = lanes_for(L);
   int grid = 0;
 #define F(K_, T_)                                                         \
@@ -474,9 +475,11 @@ struct ipclb200_pubkey {
   mutable uint32_t* d_comb = nullptr;
   mutable int comb_w = 0;
   mutable int comb_windows = 0;
+  uint8_t* d_sched_n = nullptr;  // sliding-window schedule of the exponent n
   ~ipclb200_pubkey() {
     if (d_const) cudaFree(d_const);
     if (d_comb) cudaFree(d_comb);
+    if (d_sched_n) cudaFree(d_sched_n);
   }
 };
 
@@ -496,7 +499,8 @@ struct ipclb200_privkey {
   int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
   // sliding-window schedules of the shared exponents p-1, q-1
   uint8_t* d_sched = nullptr;
-  const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr;
+  const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr,
+                *d_sched_lambda = nullptr;
   // byte-code programs of the thread-per-integer kernel and -N^-1 mod 2^256
   const uint8_t *d_prog_p = nullptr, *d_prog_q = nullptr;
   uint32_t ninv_p[8] = {}, ninv_q[8] = {};
@@ -590,6 +594,19 @@ int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
   p.exp = d_exp;
   p.exp_stride = sh_exp ? 0 : exp_words;
   p.out = d_out;
+  if (sh_exp && count >= 64 && p.exp_bits > 64) {
+    // one exponent for the whole batch (ct * scalar, ipcl/ciphertext.cpp:97-99;
+    // Miller-Rabin rounds): sliding-window schedule instead of scanning
+    const char* ns = getenv("IPCLB200_NO_SCHED");
+    if (!(ns && ns[0] == '1')) {
+      std::vector<uint8_t> sc = build_schedule(hbn::from_words(exp, exp_words), kSchedWindow);
+      uint32_t* d_sc;
+      TRY(scratch_get(8, (sc.size() + 3) / 4, &d_sc));
+      CUDA_TRY(cudaMemcpyAsync(d_sc, sc.data(), sc.size(), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));  // sc dies at scope end
+      p.sched = reinterpret_cast<const uint8_t*>(d_sc);
+    }
+  }
   TRY(launch_modexp(p, L, s));
   TRY(download_padded(out, d_out, mod_words, L, count, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -718,7 +735,13 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
     }
   } else {
     p.mode = 3;
-    p.window = pick_window(pk->nl * 32);
+    const char* ns = getenv("IPCLB200_NO_SCHED");
+    if (pk->d_sched_n && !(ns && ns[0] == '1')) {
+      p.sched_n = pk->d_sched_n;
+      p.window = kSchedWindow - 1;
+    } else {
+      p.window = pick_window(pk->nl * 32);
+    }
   }
   int grid = 0;
 #define F(K_, T_)                                                          \
@@ -965,6 +988,10 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     p.n0_stride = 0;
     p.out = d_x;
     p.count = count;
+    {
+      const char* ns = getenv("IPCLB200_NO_SCHED");
+      if (!(ns && ns[0] == '1')) p.sched = sk->d_sched_lambda;
+    }
     TRY(launch_modexp(p, L, s));
     RawFinishParams f{};
     f.x = d_x;
@@ -1182,6 +1209,12 @@ int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs,
   CUDA_TRY(cudaMalloc(&pk->d_const, blk.size() * sizeof(uint32_t)));
   CUDA_TRY(cudaMemcpy(pk->d_const, blk.data(), blk.size() * sizeof(uint32_t),
                       cudaMemcpyHostToDevice));
+  if (!hs) {
+    // non-DJN obfuscator r^n: every element has the exponent n
+    std::vector<uint8_t> sn = build_schedule(pk->n, kSchedWindow);
+    CUDA_TRY(cudaMalloc(&pk->d_sched_n, sn.size()));
+    CUDA_TRY(cudaMemcpy(pk->d_sched_n, sn.data(), sn.size(), cudaMemcpyHostToDevice));
+  }
   *out = pk.release();
   return 0;
 }
@@ -1347,16 +1380,19 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
     std::vector<uint8_t> sp = build_schedule(pm1, kSchedWindow);
     std::vector<uint8_t> sq = build_schedule(qm1, kSchedWindow);
     std::vector<uint8_t> pp = build_tile_program(sp), pq = build_tile_program(sq);
+    std::vector<uint8_t> sl = build_schedule(lam, kSchedWindow);
     std::vector<uint8_t> both(sp);
     both.insert(both.end(), sq.begin(), sq.end());
     both.insert(both.end(), pp.begin(), pp.end());
     both.insert(both.end(), pq.begin(), pq.end());
+    both.insert(both.end(), sl.begin(), sl.end());
     CUDA_TRY(cudaMalloc(&sk->d_sched, both.size()));
     CUDA_TRY(cudaMemcpy(sk->d_sched, both.data(), both.size(), cudaMemcpyHostToDevice));
     sk->d_sched_p = sk->d_sched;
     sk->d_sched_q = sk->d_sched + sp.size();
     sk->d_prog_p = sk->d_sched_q + sq.size();
     sk->d_prog_q = sk->d_prog_p + pp.size();
+    sk->d_sched_lambda = sk->d_prog_q + pq.size();
     sk->tile_slots = sp[0] + 1;
     Limbs two256 = hbn::pow2(256), inv;
     hbn::modinv(hbn::mod(psq, two256), two256, &inv);

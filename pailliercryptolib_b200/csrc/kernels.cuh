@@ -178,6 +178,9 @@ struct ModexpParams {
   uint32_t* table_ws;
   int window;
   unsigned int* work_counter;
+  // shared exponent: host-built sliding-window schedule (modexp_sched_core),
+  // nullptr = scan the exponent with the fixed window
+  const uint8_t* sched;
 };
 
 template <int K, int T>
@@ -205,9 +208,12 @@ __global__ void __launch_bounds__(kBlockThreads)
       M::load(x, p.base + ii * p.base_stride);
       M::mul(x, x, rr, n, n0inv);
     }
-    modexp_core<K, T>(acc, x, n, n0inv, p.one + ii * p.mod_stride,
-                      p.exp + ii * p.exp_stride, p.exp_words, p.exp_bits,
-                      p.window, tab);
+    if (p.sched)
+      modexp_sched_core<K, T>(acc, x, n, n0inv, p.sched, tab);
+    else
+      modexp_core<K, T>(acc, x, n, n0inv, p.one + ii * p.mod_stride,
+                        p.exp + ii * p.exp_stride, p.exp_words, p.exp_bits,
+                        p.window, tab);
     M::from_mont(x, acc, n, n0inv);
     if (valid) M::store(p.out + inst * L, x);
   }
@@ -270,6 +276,7 @@ struct EncryptParams {
   const uint32_t* nR;   // n * R mod n^2
   const uint32_t* n_exp;  // n as exponent (non-DJN), NL words
   int n_exp_words;
+  const uint8_t* sched_n;  // sliding-window schedule of n (non-DJN) or nullptr
   const uint32_t* hs_m;  // hs in Montgomery form (DJN generic path), L words
   const uint32_t* comb;  // comb table [nwin][1<<cw][L] or nullptr
   int comb_w;
@@ -356,8 +363,11 @@ __global__ void __launch_bounds__(kBlockThreads)
       load_padded<K, T>(x, p.r + ii * (size_t)p.r_words, p.r_words);
       M::load(t, p.m.rr);
       M::mul(x, x, t, n, n0inv);
-      modexp_core<K, T>(acc, x, n, n0inv, p.m.one, p.n_exp, p.n_exp_words,
-                        p.n_exp_words * 32, p.window, tab);
+      if (p.sched_n)
+        modexp_sched_core<K, T>(acc, x, n, n0inv, p.sched_n, tab);
+      else
+        modexp_core<K, T>(acc, x, n, n0inv, p.m.one, p.n_exp, p.n_exp_words,
+                          p.n_exp_words * 32, p.window, tab);
     }
     M::mul(acc, acc, gm, n, n0inv);  // obf*gm, out of Montgomery form
     canonicalize<K, T>(acc, n, n0inv, p.m.rr, p.m.small_mod);

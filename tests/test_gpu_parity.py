@@ -77,6 +77,30 @@ def test_modexp_shared_operands(capi, oracle):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("ebits", [65, 700, 2048])
+def test_modexp_shared_exponent_schedule(capi, ebits, monkeypatch):
+    """one exponent for the whole batch (IPCLB200_SHARED_EXP, count >= 64) runs
+    the host-built sliding-window schedule; same residues as the fixed-window
+    scan and as Python pow(), including exponents 2^k and 2^k - 1"""
+    rng = np.random.default_rng(ebits)
+    L, count = 64, 100
+    mod = random_limbs(rng, 1, L)
+    mod[0, 0] |= 1
+    mod[0, -1] |= 0x80000000
+    m = from_limbs(mod[0])
+    base = random_limbs(rng, count, L)
+    B = batch_from_limbs(base)
+    ew = (ebits + 31) // 32
+    for e in (int.from_bytes(rng.bytes(ew * 4), "little") >> (32 * ew - ebits) | (1 << (ebits - 1)),
+              1 << (ebits - 1), (1 << ebits) - 1):
+        el = to_limbs(e, ew)[None, :]
+        got = capi.modexp(base, el, mod, capi.SHARED_MOD | capi.SHARED_EXP)
+        assert batch_from_limbs(got) == [pow(b, e, m) for b in B]
+        monkeypatch.setenv("IPCLB200_NO_SCHED", "1")
+        assert np.array_equal(capi.modexp(base, el, mod, capi.SHARED_MOD | capi.SHARED_EXP), got)
+        monkeypatch.delenv("IPCLB200_NO_SCHED")
+
+
 def test_modexp_edge_exponents_and_batch_one(capi):
     L = 32
     m = (1 << 1023) + 1155
