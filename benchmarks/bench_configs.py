@@ -176,6 +176,42 @@ def main():
                       "roofline_frac_int": B * modexp_macs(L, bits) / (ms * 1e-3) / peak,
                       "hbm_gbs": B * 3 * L * 4 / (ms * 1e-3) / 1e9, "verified": "first 4 vs oracle"})
 
+    if "rawmg" in only:
+        # configs[4] across the GPUs of one box: a fixed total batch is cut into
+        # contiguous shards (strong scaling, no collective on the data path:
+        # every modexp is independent); time = max over ranks
+        for bits, lgs in ((1024, (10, 14, 20)), (2048, (10, 14, 18, 20)), (3072, (14, 18)),
+                          (4096, (16,))):
+            L = bits // 32
+            g = np.random.default_rng(bits)
+            mod = random_limbs(g, 1, L)
+            mod[0, 0] |= 1
+            mod[0, -1] |= 0x80000000
+            for lg in lgs:
+                total = 1 << lg
+                s0, s1 = sharding.shard_range(total, world, rank)
+                Bl = s1 - s0
+                gl = np.random.default_rng(bits * 100 + lg * 10 + rank)
+                base, exp = random_limbs(gl, Bl, L), random_limbs(gl, Bl, L)
+                d_b, d_e = dev(base, device), dev(exp, device)
+                d_o = torch.empty_like(d_b)
+                fn = lambda: capi.modexp_dev(d_b.data_ptr(), d_e.data_ptr(), mod[0], L, bits, Bl,
+                                             d_o.data_ptr(), stream)
+                fn()
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                ms = timed(fn, 2, warmup=1)
+                ms = sharding.max_over_ranks([ms], device)[0]
+                want = orc.modexp(base[:2], exp[:2], mod, shared_mod=True)
+                assert np.array_equal(host(d_o)[:2], want)
+                emit({"config": "raw modexp %d-bit, total batch 2^%d sharded over the ranks" % (bits, lg),
+                      "modexp_per_s": total / ms * 1e3, "ms": ms, "batch_per_gpu": Bl,
+                      "alg_mac32_per_op": modexp_macs(L, bits),
+                      "roofline_frac_int_per_gpu": total * modexp_macs(L, bits) / (ms * 1e-3) / peak / world,
+                      "hbm_gbs": total * 3 * L * 4 / (ms * 1e-3) / 1e9,
+                      "verified": "first 2 of every rank vs oracle"})
+
     if "cpu" in only and rank == 0:
         # CPU lines on this box's host cores, same inputs for the three
         # implementations: scalar port, restated AVX512-IFMA mb8, OpenSSL
