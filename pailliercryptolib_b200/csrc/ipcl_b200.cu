@@ -50,6 +50,9 @@ int fail(int code, const std::string& msg) {
 // size classes: modulus words -> (limbs per lane K, lanes per integer T)
 // ---------------------------------------------------------------------------
 const int kClasses[] = {16, 32, 48, 64, 96, 128, 192, 256};
+// largest number of jobs for which the wide (4 limbs per lane) layout is used
+// (measured crossovers, profiles/r01_wide_layout.md)
+constexpr size_t kWideMax32 = 8192, kWideMax64 = 4096, kWideMax128 = 2048;
 
 int class_words(int words) {
   for (int c : kClasses)
@@ -69,6 +72,35 @@ int class_words(int words) {
     case 256: F(16, 16); break;            \
     default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
   }
+
+// Small batches: the same kernels with one integer spread over four times as
+// many lanes (4 limbs per lane).  A batch that cannot fill the 148 SMs is
+// latency bound -- a modexp is ~1200-2500 dependent Montgomery products -- and
+// the wide layout shortens every product (8 multiplies per row and lane
+// instead of 32) at the price of more shuffles per multiply.
+#define IPCLB200_DISPATCH_WIDE(L, F)       \
+  switch (L) {                             \
+    case 32:  F(4, 8); break;              \
+    case 64:  F(4, 16); break;             \
+    case 128: F(4, 32); break;             \
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
+  }
+
+// tasks = independent big-integer jobs of L words in the launch
+bool use_wide(size_t tasks, int L) {
+  if (!(L == 32 || L == 64 || L == 128)) return false;
+  const char* e = getenv("IPCLB200_WIDE");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  size_t max_tasks = 0;  // measured crossover, see DESIGN.md
+  switch (L) {
+    case 32: max_tasks = kWideMax32; break;
+    case 64: max_tasks = kWideMax64; break;
+    default: max_tasks = kWideMax128; break;
+  }
+  if (const char* m = getenv("IPCLB200_WIDE_MAX")) max_tasks = strtoul(m, nullptr, 10);
+  return tasks <= max_tasks;
+}
 
 int lanes_for(int L) {
   switch (L) {
@@ -436,7 +468,11 @@ int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
                               &p.table_ws, &p.work_counter));             \
     modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
-  IPCLB200_DISPATCH(L, F)
+  if (use_wide(p.count, L)) {
+    IPCLB200_DISPATCH_WIDE(L, F)
+  } else {
+    IPCLB200_DISPATCH(L, F)
+  }
 #undef F
   (void)T;
   g_ctx.launches++;
@@ -752,7 +788,11 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
                               &p.table_ws, &p.work_counter));              \
     encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
-  IPCLB200_DISPATCH(L, F)
+  if (use_wide(count, L)) {
+    IPCLB200_DISPATCH_WIDE(L, F)
+  } else {
+    IPCLB200_DISPATCH(L, F)
+  }
 #undef F
   g_ctx.launches++;
   CUDA_TRY(cudaGetLastError());
@@ -949,7 +989,11 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
                               &p.table_ws, &p.work_counter));              \
     decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
   }
-      IPCLB200_DISPATCH(L, F)
+      if (use_wide(2 * count, L)) {
+        IPCLB200_DISPATCH_WIDE(L, F)
+      } else {
+        IPCLB200_DISPATCH(L, F)
+      }
 #undef F
       g_ctx.launches++;
     }

@@ -12,7 +12,16 @@ from pailliercryptolib_b200.limbs import (batch_from_limbs, batch_to_limbs,
 pytestmark = pytest.mark.gpu
 
 
-def test_modexp_golden_vectors(capi, modexp_vectors):
+@pytest.fixture(params=["default-layout", "wide-layout"])
+def layout(request, monkeypatch):
+    """runs a test once with the default lane layout (16 or 12 limbs per lane)
+    and once with the small-batch layout (4 limbs per lane, four times as many
+    lanes per integer); without the override the library picks by batch size"""
+    monkeypatch.setenv("IPCLB200_WIDE", "0" if request.param == "default-layout" else "1")
+    return request.param
+
+
+def test_modexp_golden_vectors(capi, modexp_vectors, layout):
     """every golden vector, one modulus per call group (heterogeneous path)"""
     by_bits = {}
     for v in modexp_vectors:
@@ -27,7 +36,7 @@ def test_modexp_golden_vectors(capi, modexp_vectors):
 
 
 @pytest.mark.parametrize("bits", [512, 1024, 1536, 2048, 3072, 4096, 6144, 8192])
-def test_modexp_random_vs_oracle(capi, oracle, bits):
+def test_modexp_random_vs_oracle(capi, oracle, bits, layout):
     """shared odd modulus with the top bit set, per-element base and exponent;
     batch sizes that are not multiples of the group count"""
     L = bits // 32
@@ -150,7 +159,7 @@ def test_modmul_vs_oracle(capi, oracle, bits):
         assert np.array_equal(got, want)
 
 
-def test_iso_kat_through_cabi(capi, iso):
+def test_iso_kat_through_cabi(capi, iso, layout):
     """The reference's only known-answer test, replayed through the C ABI:
     test_cryptography.cpp:198-240 (21 values, non-DJN key, injected r)."""
     p, q = iso["p"], iso["q"]
@@ -206,7 +215,7 @@ def test_scheme_golden_through_cabi(capi, keys, scheme_vectors, bits, monkeypatc
 
 
 @pytest.mark.parametrize("bits", ["1024", "2048", "3072"])
-def test_encrypt_decrypt_batch_vs_oracle(capi, oracle, keys, bits):
+def test_encrypt_decrypt_batch_vs_oracle(capi, oracle, keys, bits, layout):
     """larger batch: DJN through the fixed-base comb (count >= 64), non-DJN,
     decrypt CRT and RAW, all against the oracle on the same seeded inputs"""
     k = keys[bits]
