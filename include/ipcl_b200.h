@@ -189,6 +189,13 @@ uint64_t ipclb200_launch_count(void);
  * multiply pipe. */
 int ipclb200_pipe_mix(int mode, double* ms_out);
 
+/* Diagnostics for the symmetric-squaring kernel (mont_sqr.cuh): for `count`
+ * 64-word integers a (< 2^2048) and one odd 64-word modulus, out_sqr[i] =
+ * MontSqr::sqr(a[i]) and out_mul[i] = Mont::mul(a[i], a[i]); both are
+ * a^2 * 2^-2048 mod n up to a multiple of n (values below 2^2048). */
+int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
+                           uint32_t* out_sqr, uint32_t* out_mul);
+
 /* Diagnostics: the two CRT residues of every ciphertext,
  *   x[i][0] = ct[i]^(p-1) mod p^2,  x[i][1] = ct[i]^(q-1) mod q^2
  * (the modexp results of ipcl/pri_key.cpp:128-134, before the L function), as

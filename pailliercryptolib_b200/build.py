@@ -49,7 +49,7 @@ def build_cuda(force=False, verbose=False):
     """libipcl_b200.so: kernels + C ABI (nvcc, sm_100a only)."""
     srcs = [os.path.join(CSRC, f) for f in
             ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "mont_fp64.cuh",
-             "mont_tile.cuh", "hostbn.hpp")]
+             "mont_sqr.cuh", "mont_tile.cuh", "hostbn.hpp")]
     srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))
     if not force and _newer(CUDA_LIB, srcs):
         return CUDA_LIB

@@ -35,6 +35,7 @@ EXPORTS = [
     "ipclb200_pipe_mix", "ipclb200_stream", "ipclb200_dev_alloc",
     "ipclb200_dev_free", "ipclb200_dev_upload", "ipclb200_dev_download",
     "ipclb200_dev_copy", "ipclb200_sync", "ipclb200_class_words",
+    "ipclb200_debug_montsqr",
 ]
 
 
@@ -93,6 +94,15 @@ def int_peak():
     macs, mhz = ctypes.c_double(), ctypes.c_double()
     _check(lib().ipclb200_int_peak(ctypes.byref(macs), ctypes.byref(mhz)))
     return macs.value, mhz.value
+
+
+def debug_montsqr(a, mod):
+    a, mod = np.atleast_2d(_c(a)), _c(mod)
+    assert a.shape[1] == 64 and mod.shape[-1] == 64
+    s, m = np.zeros_like(a), np.zeros_like(a)
+    _check(lib().ipclb200_debug_montsqr(_p(a), _p(mod), ctypes.c_size_t(a.shape[0]),
+                                        _p(s), _p(m)))
+    return s, m
 
 
 def pipe_mix(mode):

@@ -884,7 +884,29 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     // sharing the work counter.  FP64 needs the 64-word class (2048-bit key).
     const char* mode = force ? force : "int";
     const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
-               want_dual2 = !strcmp(mode, "dual2");
+               want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
+    if (want_sqr && L == 64 && !use_wide(2 * count, L)) {
+      // symmetric squarings (mont_sqr.cuh), 64-word class
+      constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
+      static bool attr_set = false;
+      if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_sqr_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_sqr_kernel,
+                                                             kBlockThreads, smem));
+      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "sqr kernel does not fit an SM");
+      const size_t need = (2 * ((count + 7) / 8) + 3) / 4;
+      const size_t capb = (size_t)per_sm * g_ctx.sms;
+      const int grid = (int)(need < capb ? need : capb);
+      TRY(table_ws_with_counter(s, (size_t)grid * 32 * L * p.table_entries, &p.table_ws,
+                                &p.work_counter));
+      decrypt_crt_sqr_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+      g_ctx.launches++;
+      CUDA_TRY(cudaGetLastError());
+    } else
     if ((want_fp || want_dual || want_dual2) && sk->fp_ok && L == kFpWords) {
       constexpr int FL = kFpLimbs;
       constexpr size_t smem = fp_role_smem(kFpK, kFpT);
@@ -1642,6 +1664,44 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_ctx.device);
     *sm_clock_mhz = khz / 1000.0;
   }
+  return 0;
+}
+
+int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
+                           uint32_t* out_sqr, uint32_t* out_mul) {
+  if (!a || !mod || !out_sqr || !out_mul)
+    return fail(IPCLB200_ERR_BAD_ARG, "debug_montsqr: null pointer");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int L = 64;
+  Limbs n;
+  TRY(check_modulus(mod, L, &n));
+  std::shared_ptr<DevModulus> dm;
+  TRY(make_modulus(n, L, &dm));
+  uint32_t *d_a, *d_s, *d_m;
+  TRY(scratch_get(0, count * (size_t)L, &d_a));
+  TRY(scratch_get(1, count * (size_t)L, &d_s));
+  TRY(scratch_get(2, count * (size_t)L, &d_m));
+  CUDA_TRY(cudaMemcpyAsync(d_a, a, count * (size_t)L * 4, cudaMemcpyHostToDevice, s));
+  MontSqrTestParams p{};
+  p.a = d_a;
+  p.n = dm->mc.n;
+  p.n0inv = dm->mc.n0inv;
+  p.out_sqr = d_s;
+  p.out_mul = d_m;
+  p.count = count;
+  constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
+  CUDA_TRY(cudaFuncSetAttribute(montsqr_test_kernel,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)((count + 31) / 32);
+  montsqr_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out_sqr, d_s, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(out_mul, d_m, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
   return 0;
 }
 

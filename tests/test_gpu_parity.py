@@ -306,6 +306,40 @@ def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     assert np.array_equal(alt, pt)
 
 
+def test_symmetric_squaring_kernel(capi, keys, monkeypatch):
+    """MontSqr::sqr (mont_sqr.cuh, opt-in IPCLB200_DECRYPT=sqr): single
+    squarings are a^2 * 2^-2048 mod n below 2^2048 for edge values and random
+    ones, and the decrypt kernel built on it leaves the same residues as the
+    default kernel and as Python pow()"""
+    rng = np.random.default_rng(4096)
+    R = 1 << 2048
+    mod = random_limbs(rng, 1, 64)
+    mod[0, 0] |= 1
+    mod[0, -1] |= 0x80000000
+    n = from_limbs(mod[0])
+    vals = [0, 1, R - 1, n - 1, n, int("ffffffff00000000" * 32, 16)] + \
+        [int.from_bytes(rng.bytes(256), "little") for _ in range(70)]
+    s, m = capi.debug_montsqr(batch_to_limbs(vals, 64), mod[0])
+    for got in (batch_from_limbs(s), batch_from_limbs(m)):
+        assert all(x < R and (x * R - v * v) % n == 0 for x, v in zip(got, vals))
+    k = keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    nsq = (p * q) ** 2
+    count = 2500  # above the wide-layout threshold: the 16x4 kernels run
+    cts = [int.from_bytes(rng.bytes(512), "little") % nsq for _ in range(count)]
+    cts[:4] = [0, 1, nsq - 1, p * 999]
+    ct = batch_to_limbs(cts, 128)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    monkeypatch.setenv("IPCLB200_DECRYPT", "int")
+    base = sk.crt_residues(ct)
+    monkeypatch.setenv("IPCLB200_DECRYPT", "sqr")
+    x = sk.crt_residues(ct)
+    assert np.array_equal(x, base)
+    for i in range(40):
+        assert from_limbs(x[i, 0]) == pow(cts[i], p - 1, p * p)
+        assert from_limbs(x[i, 1]) == pow(cts[i], q - 1, q * q)
+
+
 FP_CONFIGS = [
     ("int", {}),
     ("fp", {"IPCLB200_FP_BLOCKS": "2"}),
