@@ -52,7 +52,9 @@ int fail(int code, const std::string& msg) {
 const int kClasses[] = {16, 32, 48, 64, 96, 128, 192, 256};
 // largest number of jobs for which the wide (4 limbs per lane) layout is used
 // (measured crossovers, profiles/r01_wide_layout.md)
-constexpr size_t kWideMax32 = 8192, kWideMax64 = 4096, kWideMax128 = 2048;
+constexpr size_t kWideMax32 = 6144, kWideMax64 = 3072, kWideMax128 = 1536;
+// ... and for the middle layout (8 limbs per lane)
+constexpr size_t kMidMax32 = 12288, kMidMax64 = 6144, kMidMax128 = 3072;
 
 int class_words(int words) {
   for (int c : kClasses)
@@ -86,20 +88,39 @@ int class_words(int words) {
     default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
   }
 
-// tasks = independent big-integer jobs of L words in the launch
-bool use_wide(size_t tasks, int L) {
-  if (!(L == 32 || L == 64 || L == 128)) return false;
-  const char* e = getenv("IPCLB200_WIDE");
-  if (e && e[0] == '0') return false;
-  if (e && e[0] == '1') return true;
-  size_t max_tasks = 0;  // measured crossover, see DESIGN.md
-  switch (L) {
-    case 32: max_tasks = kWideMax32; break;
-    case 64: max_tasks = kWideMax64; break;
-    default: max_tasks = kWideMax128; break;
+// in between: 8 limbs per lane, twice the default number of lanes
+#define IPCLB200_DISPATCH_MID(L, F)        \
+  switch (L) {                             \
+    case 32:  F(8, 4); break;              \
+    case 64:  F(8, 8); break;              \
+    case 128: F(8, 16); break;             \
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
   }
-  if (const char* m = getenv("IPCLB200_WIDE_MAX")) max_tasks = strtoul(m, nullptr, 10);
-  return tasks <= max_tasks;
+
+// 0 = default layout, 1 = wide (4 limbs per lane), 2 = middle (8 limbs per
+// lane); tasks = independent big-integer jobs of L words in the launch
+int pick_layout(size_t tasks, int L);
+bool use_wide(size_t tasks, int L) { return pick_layout(tasks, L) == 1; }
+
+int pick_layout(size_t tasks, int L) {
+  if (!(L == 32 || L == 64 || L == 128)) return 0;
+  const char* e = getenv("IPCLB200_WIDE");
+  if (e && e[0] == '0') return 0;
+  if (e && e[0] == '1') return 1;
+  if (e && e[0] == '2') return 2;
+  {
+    size_t wide_max = 0, mid_max = 0;
+    switch (L) {
+      case 32: wide_max = kWideMax32; mid_max = kMidMax32; break;
+      case 64: wide_max = kWideMax64; mid_max = kMidMax64; break;
+      default: wide_max = kWideMax128; mid_max = kMidMax128; break;
+    }
+    if (const char* m = getenv("IPCLB200_WIDE_MAX")) wide_max = strtoul(m, nullptr, 10);
+    if (const char* m = getenv("IPCLB200_MID_MAX")) mid_max = strtoul(m, nullptr, 10);
+    if (tasks <= wide_max) return 1;
+    if (tasks <= mid_max) return 2;
+    return 0;
+  }
 }
 
 int lanes_for(int L) {
@@ -468,10 +489,10 @@ int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
                               &p.table_ws, &p.work_counter));             \
     modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
-  if (use_wide(p.count, L)) {
-    IPCLB200_DISPATCH_WIDE(L, F)
-  } else {
-    IPCLB200_DISPATCH(L, F)
+  switch (pick_layout(p.count, L)) {
+    case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
+    case 2: IPCLB200_DISPATCH_MID(L, F) break;
+    default: IPCLB200_DISPATCH(L, F)
   }
 #undef F
   (void)T;
@@ -788,10 +809,10 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
                               &p.table_ws, &p.work_counter));              \
     encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
   }
-  if (use_wide(count, L)) {
-    IPCLB200_DISPATCH_WIDE(L, F)
-  } else {
-    IPCLB200_DISPATCH(L, F)
+  switch (pick_layout(count, L)) {
+    case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
+    case 2: IPCLB200_DISPATCH_MID(L, F) break;
+    default: IPCLB200_DISPATCH(L, F)
   }
 #undef F
   g_ctx.launches++;
@@ -885,7 +906,7 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     const char* mode = force ? force : "int";
     const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
                want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
-    if (want_sqr && L == 64 && !use_wide(2 * count, L)) {
+    if (want_sqr && L == 64 && pick_layout(2 * count, L) == 0) {
       // symmetric squarings (mont_sqr.cuh), 64-word class
       constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
       static bool attr_set = false;
@@ -1011,10 +1032,10 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
                               &p.table_ws, &p.work_counter));              \
     decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
   }
-      if (use_wide(2 * count, L)) {
-        IPCLB200_DISPATCH_WIDE(L, F)
-      } else {
-        IPCLB200_DISPATCH(L, F)
+      switch (pick_layout(2 * count, L)) {
+        case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
+        case 2: IPCLB200_DISPATCH_MID(L, F) break;
+        default: IPCLB200_DISPATCH(L, F)
       }
 #undef F
       g_ctx.launches++;

@@ -12,12 +12,14 @@ from pailliercryptolib_b200.limbs import (batch_from_limbs, batch_to_limbs,
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["default-layout", "wide-layout"])
+@pytest.fixture(params=["default-layout", "wide-layout", "mid-layout"])
 def layout(request, monkeypatch):
-    """runs a test once with the default lane layout (16 or 12 limbs per lane)
-    and once with the small-batch layout (4 limbs per lane, four times as many
-    lanes per integer); without the override the library picks by batch size"""
-    monkeypatch.setenv("IPCLB200_WIDE", "0" if request.param == "default-layout" else "1")
+    """runs a test with the default lane layout (16 or 12 limbs per lane), the
+    small-batch layout (4 limbs per lane, four times as many lanes per integer)
+    and the one in between (8 limbs per lane); without the override the library
+    picks by batch size"""
+    monkeypatch.setenv("IPCLB200_WIDE", {"default-layout": "0", "wide-layout": "1",
+                                         "mid-layout": "2"}[request.param])
     return request.param
 
 

@@ -36,7 +36,7 @@ def timed(fn, reps=5):
     return best
 
 
-counts = [8, 64, 256, 1024, 2048, 4096, 8192]
+counts = [256, 1024, 2048, 3072, 4096, 6144, 8192, 12288, 16384]
 for bits in ("2048", "1024"):
     k = K[bits]
     p, q = sorted((k["p"], k["q"]))
@@ -52,7 +52,7 @@ for bits in ("2048", "1024"):
         d_dt = torch.empty((B, NL), dtype=torch.int32, device=dev)
         d_o = torch.empty((B, 2 * NL), dtype=torch.int32, device=dev)
         res = {}
-        for wide in ("0", "1"):
+        for wide in ("0", "2", "1"):
             os.environ["IPCLB200_WIDE"] = wide
             enc = timed(lambda: pk.encrypt_dev(d_pt.data_ptr(), NL, d_r.data_ptr(), NL // 2, B,
                                                d_ct.data_ptr(), st))
@@ -62,7 +62,8 @@ for bits in ("2048", "1024"):
             mul = timed(lambda: capi.modexp_dev(d_ct.data_ptr(), d_e.data_ptr(), nsq, NL, 32 * NL, B,
                                                 d_o.data_ptr(), st), reps=2)
             res[wide] = (enc, dec, mul, ct, d_o.clone())
-        assert torch.equal(res["0"][3], res["1"][3]) and torch.equal(res["0"][4], res["1"][4])
-        print("key %s batch %5d | encrypt %7.3f -> %7.3f ms | decrypt %7.3f -> %7.3f ms | ct*pt(%s-bit) %8.3f -> %8.3f ms"
-              % (bits, B, res["0"][0], res["1"][0], res["0"][1], res["1"][1], bits, res["0"][2],
-                 res["1"][2]), flush=True)
+        for w in ("1", "2"):
+            assert torch.equal(res["0"][3], res[w][3]) and torch.equal(res["0"][4], res[w][4])
+        print("key %s batch %5d | encrypt %7.3f / %7.3f / %7.3f ms | decrypt %7.3f / %7.3f / %7.3f ms | ct*pt %8.3f / %8.3f / %8.3f ms   (default / mid / wide)"
+              % (bits, B, res["0"][0], res["2"][0], res["1"][0], res["0"][1], res["2"][1], res["1"][1],
+                 res["0"][2], res["2"][2], res["1"][2]), flush=True)
