@@ -906,7 +906,41 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     const char* mode = force ? force : "int";
     const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
                want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
-    if (want_sqr && L == 64 && pick_layout(2 * count, L) == 0) {
+    if (!strcmp(mode, "sqr2") && L == 64 && pick_layout(2 * count, L) == 0) {
+      // symmetric squarings in the 32 x 2 layout (MontSqr2)
+      constexpr size_t smem = sqr2_smem_bytes(kBlockThreads);
+      static bool attr_set2 = false;
+      if (!attr_set2) {
+        CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_sqr2_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set2 = true;
+      }
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_sqr2_kernel,
+                                                             kBlockThreads, smem));
+      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "sqr2 kernel does not fit an SM");
+      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
+      const size_t capb = (size_t)per_sm * g_ctx.sms;
+      const int grid = (int)(need < capb ? need : capb);
+      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
+                                &p.work_counter));
+      decrypt_crt_sqr2_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+      g_ctx.launches++;
+      CUDA_TRY(cudaGetLastError());
+    } else if (!strcmp(mode, "k32") && L == 64) {
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_k32_kernel,
+                                                             kBlockThreads, 0));
+      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "k32 kernel does not fit an SM");
+      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
+      const size_t capb = (size_t)per_sm * g_ctx.sms;
+      const int grid = (int)(need < capb ? need : capb);
+      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
+                                &p.work_counter));
+      decrypt_crt_k32_kernel<<<grid, kBlockThreads, 0, s>>>(p);
+      g_ctx.launches++;
+      CUDA_TRY(cudaGetLastError());
+    } else if (want_sqr && L == 64 && pick_layout(2 * count, L) == 0) {
       // symmetric squarings (mont_sqr.cuh), 64-word class
       constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
       static bool attr_set = false;
@@ -1713,11 +1747,20 @@ int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
   p.out_sqr = d_s;
   p.out_mul = d_m;
   p.count = count;
-  constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
-  CUDA_TRY(cudaFuncSetAttribute(montsqr_test_kernel,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)((count + 31) / 32);
-  montsqr_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+  const char* lay = getenv("IPCLB200_DEBUG_SQR_LAYOUT");
+  if (lay && lay[0] == '2') {
+    constexpr size_t smem = sqr2_smem_bytes(kBlockThreads);
+    CUDA_TRY(cudaFuncSetAttribute(montsqr2_test_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)((count + 63) / 64);
+    montsqr2_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+  } else {
+    constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
+    CUDA_TRY(cudaFuncSetAttribute(montsqr_test_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)((count + 31) / 32);
+    montsqr_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
+  }
   g_ctx.launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out_sqr, d_s, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));

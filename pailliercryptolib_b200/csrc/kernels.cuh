@@ -546,6 +546,14 @@ __global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
   decrypt_int_role<K, T>(p, blockIdx.x * gpb + threadIdx.x / T);
 }
 
+// experiment: the 64-word class as 32 limbs x 2 lanes (half the shuffles and
+// row bookkeeping per multiply, 246 registers -> 2 blocks per SM)
+__global__ void __launch_bounds__(kBlockThreads, 2)
+    decrypt_crt_k32_kernel(const DecryptCrtParams p) {
+  const size_t gpb = blockDim.x / 2;
+  decrypt_int_role<32, 2>(p, blockIdx.x * gpb + threadIdx.x / 2);
+}
+
 // --------------------------------------------------------------------------
 // K4s: the CRT-decrypt modexp with symmetric squarings (mont_sqr.cuh): the
 // squarings of the schedule (85 % of the products) go through MontSqr::sqr
@@ -632,6 +640,82 @@ __global__ void __launch_bounds__(kBlockThreads, 3)
   }
 }
 
+// the same with the 32 x 2 layout (MontSqr2): half the lanes per integer, so
+// half the recombination work per integer
+__global__ void __launch_bounds__(kBlockThreads, 2)
+    decrypt_crt_sqr2_kernel(const DecryptCrtParams p) {
+  constexpr int K = 32, T = 2;
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  constexpr int GW = 32 / T;
+  extern __shared__ uint32_t sqr_smem[];
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  uint32_t* gs = sqr_smem + (threadIdx.x / T) * kSq2GroupWords;
+  uint32_t* zero = sqr_smem + gpb * kSq2GroupWords;
+  MontSqr::sqr_init(sqr_smem, (int)(gpb * kSq2GroupWords + 32));
+  uint32_t* tab = p.table_ws + gid * ((size_t)L * p.table_entries);
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= 2u * nchunks) break;
+    const int side = (int)(w & 1u);
+    const size_t inst = (size_t)(w >> 1) * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const uint32_t* mn = side ? p.m1.n : p.m0.n;
+    const uint32_t* mr3 = side ? p.m1.r3 : p.m0.r3;
+    const uint32_t n0inv = side ? p.m1.n0inv : p.m0.n0inv;
+    const uint8_t* sched = side ? p.sched1 : p.sched0;
+    uint32_t n[K];
+    M::load(n, mn);
+    const uint32_t* c = p.ct + ii * (size_t)(2 * L);
+    uint32_t x[K], acc[K];
+    {
+      uint32_t lo[K], hi[K], t[K];
+      M::load(lo, c);
+      M::load(hi, c + L);
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = 0;
+      if (M::lane_t() == 0) t[0] = 1;
+      M::mul(lo, lo, t, n, n0inv);
+      uint32_t cy = M::group_add(lo, hi, 0u);
+      if (__any_sync(IPCLB200_FULL_MASK, cy)) M::cond_sub_n(lo, n, cy);
+      M::load(t, mr3);
+      M::mul(x, lo, t, n, n0inv);
+    }
+    const int nodd = sched[0];
+    {
+      uint32_t t[K], x2[K];
+      M::store(tab, x);
+      MontSqr2::sqr(x2, x, n, n0inv, gs, zero);
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = x[j];
+      for (int i = 1; i < nodd; i++) {
+        M::mul(t, t, x2, n, n0inv);
+        M::store(tab + (size_t)i * L, t);
+      }
+    }
+    M::load(acc, tab + (size_t)sched[1] * L);
+    const uint8_t* op = sched + 2;
+#pragma unroll 1
+    for (uint32_t o = __ldg(op); o != 0xffu; o = __ldg(++op)) {
+      if (o) {
+        uint32_t b[K];
+        M::load(b, tab + (size_t)(o - 1) * L);
+        M::mul(acc, acc, b, n, n0inv);
+      } else {
+        MontSqr2::sqr(acc, acc, n, n0inv, gs, zero);
+      }
+    }
+    M::from_mont(x, acc, n, n0inv);
+    if (valid) M::store(p.x + (inst * 2 + side) * L, x);
+  }
+}
+
+__global__ void __launch_bounds__(kBlockThreads, 2)
+    montsqr2_test_kernel(const struct MontSqrTestParams p);
+
 // test kernel: out_sqr = MontSqr::sqr(a), out_mul = Mont::mul(a, a), one
 // 64-word integer per group
 struct MontSqrTestParams {
@@ -659,6 +743,27 @@ __global__ void __launch_bounds__(kBlockThreads, 2)
   M::load(n, p.n);
   M::load(a, p.a + ii * L);
   MontSqr::sqr(r, a, n, p.n0inv, gs, zero);
+  if (valid) M::store(p.out_sqr + ii * L, r);
+  M::mul(r, a, a, n, p.n0inv);
+  if (valid) M::store(p.out_mul + ii * L, r);
+}
+
+__global__ void __launch_bounds__(kBlockThreads, 2)
+    montsqr2_test_kernel(const MontSqrTestParams p) {
+  constexpr int K = 32, T = 2, L = 64;
+  using M = Mont<K, T>;
+  extern __shared__ uint32_t sqr_smem[];
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  uint32_t* gs = sqr_smem + (threadIdx.x / T) * kSq2GroupWords;
+  uint32_t* zero = sqr_smem + gpb * kSq2GroupWords;
+  MontSqr::sqr_init(sqr_smem, (int)(gpb * kSq2GroupWords + 32));
+  const bool valid = gid < p.count;
+  const size_t ii = valid ? gid : p.count - 1;
+  uint32_t n[K], a[K], r[K];
+  M::load(n, p.n);
+  M::load(a, p.a + ii * L);
+  MontSqr2::sqr(r, a, n, p.n0inv, gs, zero);
   if (valid) M::store(p.out_sqr + ii * L, r);
   M::mul(r, a, a, n, p.n0inv);
   if (valid) M::store(p.out_mul + ii * L, r);

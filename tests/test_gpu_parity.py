@@ -308,8 +308,10 @@ def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     assert np.array_equal(alt, pt)
 
 
-def test_symmetric_squaring_kernel(capi, keys, monkeypatch):
-    """MontSqr::sqr (mont_sqr.cuh, opt-in IPCLB200_DECRYPT=sqr): single
+@pytest.mark.parametrize("sq_layout,mode", [("1", "sqr"), ("2", "sqr2")])
+def test_symmetric_squaring_kernel(capi, keys, monkeypatch, sq_layout, mode):
+    """MontSqr::sqr / MontSqr2::sqr (mont_sqr.cuh, opt-in IPCLB200_DECRYPT=sqr|sqr2,
+    16x4 and 32x2 lane layouts; k32 = the plain CIOS kernel at 32x2): single
     squarings are a^2 * 2^-2048 mod n below 2^2048 for edge values and random
     ones, and the decrypt kernel built on it leaves the same residues as the
     default kernel and as Python pow()"""
@@ -321,6 +323,7 @@ def test_symmetric_squaring_kernel(capi, keys, monkeypatch):
     n = from_limbs(mod[0])
     vals = [0, 1, R - 1, n - 1, n, int("ffffffff00000000" * 32, 16)] + \
         [int.from_bytes(rng.bytes(256), "little") for _ in range(70)]
+    monkeypatch.setenv("IPCLB200_DEBUG_SQR_LAYOUT", sq_layout)
     s, m = capi.debug_montsqr(batch_to_limbs(vals, 64), mod[0])
     for got in (batch_from_limbs(s), batch_from_limbs(m)):
         assert all(x < R and (x * R - v * v) % n == 0 for x, v in zip(got, vals))
@@ -334,9 +337,11 @@ def test_symmetric_squaring_kernel(capi, keys, monkeypatch):
     sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
     monkeypatch.setenv("IPCLB200_DECRYPT", "int")
     base = sk.crt_residues(ct)
-    monkeypatch.setenv("IPCLB200_DECRYPT", "sqr")
+    monkeypatch.setenv("IPCLB200_DECRYPT", mode)
     x = sk.crt_residues(ct)
     assert np.array_equal(x, base)
+    monkeypatch.setenv("IPCLB200_DECRYPT", "k32")
+    assert np.array_equal(sk.crt_residues(ct), base)
     for i in range(40):
         assert from_limbs(x[i, 0]) == pow(cts[i], p - 1, p * p)
         assert from_limbs(x[i, 1]) == pow(cts[i], q - 1, q * q)

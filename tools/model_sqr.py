@@ -253,8 +253,158 @@ def mont_sqr(a_int, n_int):
     return r
 
 
+# ---------------------------------------------------------------------------
+# the 32 x 2 layout (MontSqr2): lane t holds A_t (32 limbs), a = A0 + A1 X
+#   D_t = A_t^2 (in-lane symmetric, 528 multiplies)
+#   C_t = 2 A0 * A1[16t .. 16t+16)  (512 multiplies; lane 1 reads A0 from shared memory)
+# ---------------------------------------------------------------------------
+def blockmul_g(V, rows):
+    """generic static block product: len(V) even, any number of rows"""
+    kv = len(V) // 2
+    n_out = len(rows) + len(V)
+    e = [0] * (n_out + 4)
+    o = [0] * (n_out + 4)
+    ce = [0] * (n_out // 2 + 4)
+    co = [0] * (n_out // 2 + 4)
+
+    def chain(arr, first_word, vs, b, cnt, ci):
+        c = 0
+        for s_, v in enumerate(vs):
+            m = first_word + s_
+            w = (arr[2 * m] | (arr[2 * m + 1] << 32)) + v * b + c
+            c = w >> 64
+            w &= M64
+            arr[2 * m], arr[2 * m + 1] = w & M32, w >> 32
+        cnt[ci] += c
+
+    for i, b in enumerate(rows):
+        r = i // 2
+        if i % 2 == 0:
+            chain(e, r, [V[2 * s_] for s_ in range(kv)], b, ce, r + kv)
+            chain(o, r, [V[2 * s_ + 1] for s_ in range(kv)], b, co, r + kv)
+        else:
+            chain(e, r + 1, [V[2 * s_ + 1] for s_ in range(kv)], b, ce, r + kv + 1)
+            chain(o, r, [V[2 * s_] for s_ in range(kv)], b, co, r + kv)
+    res = []
+    c = 0
+    for p in range(n_out + 1):
+        t = e[p] + (o[p - 1] if p >= 1 else 0) + c
+        res.append(t & M32)
+        c = t >> 32
+    assert c == 0
+    c = 0
+    for p in range(n_out + 1):
+        cnt = ce[p // 2] if p % 2 == 0 else co[p // 2]
+        t = res[p] + cnt + c
+        res[p] = t & M32
+        c = t >> 32
+    assert c == 0
+    assert val(res) == val(V) * val(rows)
+    return res
+
+
+def diag_square_g(V):
+    n = len(V)
+    e = [0] * (2 * n + 4)
+    o = [0] * (2 * n + 4)
+    ce = [0] * (n + 4)
+    co = [0] * (n + 4)
+    for i in range(n - 1):
+        for start, arr, cnt, odd in ((i + 1, o, co, 1), (i + 2, e, ce, 0)):
+            js = list(range(start, n, 2))
+            c = 0
+            m = None
+            for j in js:
+                m = (i + j - odd) // 2
+                w = (arr[2 * m] | (arr[2 * m + 1] << 32)) + V[i] * V[j] + c
+                c = w >> 64
+                w &= M64
+                arr[2 * m], arr[2 * m + 1] = w & M32, w >> 32
+            if js:
+                cnt[m + 1] += c
+    s = []
+    c = 0
+    for p in range(2 * n):
+        t = e[p] + (o[p - 1] if p >= 1 else 0) + c
+        s.append(t & M32)
+        c = t >> 32
+    assert c == 0
+    c = 0
+    for p in range(2 * n):
+        cnt = ce[p // 2] if p % 2 == 0 else co[p // 2]
+        t = s[p] + cnt + c
+        s[p] = t & M32
+        c = t >> 32
+    assert c == 0
+    d = [((s[p] << 1) | (s[p - 1] >> 31 if p else 0)) & M32 for p in range(2 * n)]
+    c = 0
+    for i in range(n):
+        w = (d[2 * i] | (d[2 * i + 1] << 32)) + V[i] * V[i] + c
+        c = w >> 64
+        w &= M64
+        d[2 * i], d[2 * i + 1] = w & M32, w >> 32
+    assert c == 0 and val(d) == val(V) ** 2
+    return d
+
+
+# shared-memory words of one group in the 32 x 2 layout: a (64), then per lane
+# a D slot (64 limbs) and a C slot (64 limbs + extra word + pad = 68)
+SQ2_D = lambda t: 64 + 132 * t
+SQ2_C = lambda t: 64 + 132 * t + 64
+SQ2_CHUNK = {0: [SQ2_D(0)], 1: [SQ2_D(0) + 32, SQ2_C(0), SQ2_C(1)],
+             2: [SQ2_D(1), SQ2_C(0) + 32, SQ2_C(1) + 32], 3: [SQ2_D(1) + 32]}
+SQ2_EXTRA = {0: [], 1: [], 2: [], 3: [SQ2_C(1) + 64]}
+
+
+def sqr2_product(a_int):
+    a = limbs(a_int, 64)
+    A = [a[:32], a[32:]]
+    mem = [0] * 332
+    for t in range(2):
+        d = diag_square_g(A[t])
+        mem[SQ2_D(t):SQ2_D(t) + 64] = d
+        rows = A[1][16 * t:16 * t + 16]
+        c = double(blockmul_g(A[0], rows), 49)
+        off = SQ2_C(t) + 16 * t
+        mem[off:off + 49] = c
+    piece, cnt = {}, {}
+    for h in range(4):
+        acc = [0] * 32
+        c_out = 0
+        for off in SQ2_CHUNK[h]:
+            c = 0
+            for j in range(32):
+                v = acc[j] + mem[off + j] + c
+                acc[j] = v & M32
+                c = v >> 32
+            c_out += c
+        c = sum(mem[off] for off in SQ2_EXTRA[h])
+        for j in range(32):
+            v = acc[j] + c
+            acc[j] = v & M32
+            c = v >> 32
+        c_out += c
+        piece[h], cnt[h] = acc, c_out
+    carry = 0
+    full = []
+    for h in range(4):
+        c = carry
+        for j in range(32):
+            v = piece[h][j] + c
+            piece[h][j] = v & M32
+            c = v >> 32
+        carry = cnt[h] + c
+        full += piece[h]
+    assert carry == 0 and val(full) == a_int * a_int
+    return full
+
+
 def main():
     rnd = random.Random(16)
+    for a in [(1 << 2048) - 1, 0, int("ffffffff00000000" * 32, 16)] + \
+            [rnd.getrandbits(2048) for _ in range(12)]:
+        sqr2_product(a)
+    print("model_sqr (32 x 2 layout): ok")
     for trial in range(30):
         if trial == 0:
             a = (1 << 2048) - 1

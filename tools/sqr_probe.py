@@ -17,6 +17,9 @@ capi.init(0)
 rng = np.random.default_rng(64)
 R = 1 << 2048
 ok = True
+LAYOUT = sys.argv[1] if len(sys.argv) > 1 else "1"
+MODE = "sqr2" if LAYOUT == "2" else "sqr"
+os.environ["IPCLB200_DEBUG_SQR_LAYOUT"] = LAYOUT
 for trial in range(3):
     mod = random_limbs(rng, 1, 64)
     mod[0, 0] |= 1
@@ -62,7 +65,7 @@ if ok:
     cts = [int.from_bytes(rng.bytes(512), "little") % nsq for _ in range(count)]
     cts[:5] = [0, 1, nsq - 1, p * 12345, q * q * 3 % nsq]
     ct = batch_to_limbs(cts, 128)
-    os.environ["IPCLB200_DECRYPT"] = "sqr"
+    os.environ["IPCLB200_DECRYPT"] = MODE
     os.environ["IPCLB200_WIDE"] = "0"
     x = sk.crt_residues(ct)
     bad = [(i, s_) for i in range(300) for s_ in (0, 1)
@@ -84,7 +87,7 @@ if ok:
     d_ct = torch.empty((B, 128), dtype=torch.int32, device=dev)
     d_dt = torch.empty((B, 64), dtype=torch.int32, device=dev)
     pk.encrypt_dev(d_pt.data_ptr(), 64, d_r.data_ptr(), 32, B, d_ct.data_ptr(), st)
-    for mode in ("int", "sqr"):
+    for mode in ("int", MODE, "k32"):
         os.environ["IPCLB200_DECRYPT"] = mode
         ms = []
         for rep in range(4):
