@@ -1770,7 +1770,7 @@ int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
 }
 
 int ipclb200_pipe_mix(int mode, double* ms_out) {
-  if (mode < 0 || mode > 4 || !ms_out)
+  if (mode < 0 || mode > 8 || !ms_out)
     return fail(IPCLB200_ERR_BAD_ARG, "pipe_mix: bad argument");
   std::lock_guard<std::mutex> lk(g_ctx.mu);
   TRY(ensure_init_locked());

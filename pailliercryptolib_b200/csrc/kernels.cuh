@@ -1356,6 +1356,44 @@ __global__ void int_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
 __global__ void pipe_mix_kernel(uint32_t* out, int mode, int iters, uint32_t a,
                                 double da) {
   const int warp = threadIdx.x >> 5;
+  // modes 5-8: the second role is an ALU-pipe stream instead of DFMA:
+  // 5 = IMAD.WIDE warps + add-with-carry chains (IADD3.X), 6 = those chains
+  // alone, 7 = IMAD.WIDE warps + independent LOP3/SHF, 8 = those alone
+  if (mode >= 5) {
+    const bool alu_role = (warp >> 2) & 1;
+    if ((mode == 6 || mode == 8) && !alu_role) return;
+    if (alu_role) {
+      uint32_t v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = threadIdx.x * 7 + i;
+      uint32_t x = a + threadIdx.x;
+      if (mode <= 6) {
+        for (int it = 0; it < iters; it++) {
+          add_cc(v[0], v[0], x);
+#pragma unroll
+          for (int i = 1; i < 15; i++) addc_cc(v[i], v[i], x);
+          addc(v[15], v[15], x);
+          add_cc(v[0], v[0], v[15]);
+#pragma unroll
+          for (int i = 1; i < 15; i++) addc_cc(v[i], v[i], x);
+          addc(v[15], v[15], x);
+        }
+      } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = __funnelshift_l(v[i], x, 3) ^ v[(i + 1) & 15];
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = (v[i] & x) | (v[(i + 5) & 15] >> 1);
+        }
+      }
+      uint32_t s2 = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) s2 ^= v[i];
+      out[blockIdx.x * blockDim.x + threadIdx.x] = s2;
+      return;
+    }
+    mode = 3;  // integer role below, the other warps have returned
+  }
   const bool fp_role = mode == 1 || (mode >= 2 && ((warp >> 2) & 1));
   if ((mode == 3 && fp_role) || (mode == 4 && !fp_role)) return;
   uint32_t s = 0;
