@@ -906,7 +906,30 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     const char* mode = force ? force : "int";
     const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
                want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
-    if (!strcmp(mode, "sqr2") && L == 64 && pick_layout(2 * count, L) == 0) {
+    if ((!strcmp(mode, "k32s") || !strcmp(mode, "k32s2")) && L == 64) {
+      // 32 x 2 layout, multiplier rows from shared memory; 3 (or 2) blocks per SM
+      const bool three = !strcmp(mode, "k32s");
+      const size_t smem = (size_t)(kBlockThreads / 2) * kSbGroupWords * sizeof(uint32_t);
+      int per_sm = 0;
+      if (three)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, decrypt_crt_k32s_kernel<3>, kBlockThreads, smem));
+      else
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, decrypt_crt_k32s_kernel<2>, kBlockThreads, smem));
+      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "k32s kernel does not fit an SM");
+      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
+      const size_t capb = (size_t)per_sm * g_ctx.sms;
+      const int grid = (int)(need < capb ? need : capb);
+      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
+                                &p.work_counter));
+      if (three)
+        decrypt_crt_k32s_kernel<3><<<grid, kBlockThreads, smem, s>>>(p);
+      else
+        decrypt_crt_k32s_kernel<2><<<grid, kBlockThreads, smem, s>>>(p);
+      g_ctx.launches++;
+      CUDA_TRY(cudaGetLastError());
+    } else if (!strcmp(mode, "sqr2") && L == 64 && pick_layout(2 * count, L) == 0) {
       // symmetric squarings in the 32 x 2 layout (MontSqr2)
       constexpr size_t smem = sqr2_smem_bytes(kBlockThreads);
       static bool attr_set2 = false;

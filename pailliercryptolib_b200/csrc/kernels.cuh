@@ -554,6 +554,86 @@ __global__ void __launch_bounds__(kBlockThreads, 2)
   decrypt_int_role<32, 2>(p, blockIdx.x * gpb + threadIdx.x / 2);
 }
 
+// experiment: 32 x 2 layout with the multiplier streamed from shared memory
+// (Mont::mul_sb), so that the kernel fits 168 registers = 12 warps per SM
+constexpr int kSbGroupWords = 68;  // 64 limbs + pad (bank spread)
+template <int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB)
+    decrypt_crt_k32s_kernel(const DecryptCrtParams p) {
+  constexpr int K = 32, T = 2;
+  using M = Mont<K, T>;
+  constexpr int L = K * T;
+  constexpr int GW = 32 / T;
+  extern __shared__ uint32_t sb_smem[];
+  const size_t gpb = blockDim.x / T;
+  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
+  uint32_t* bsm = sb_smem + (threadIdx.x / T) * kSbGroupWords;
+  uint32_t* tab = p.table_ws + gid * ((size_t)L * p.table_entries);
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= 2u * nchunks) break;
+    const int side = (int)(w & 1u);
+    const size_t inst = (size_t)(w >> 1) * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const uint32_t* mn = side ? p.m1.n : p.m0.n;
+    const uint32_t* mr3 = side ? p.m1.r3 : p.m0.r3;
+    const uint32_t n0inv = side ? p.m1.n0inv : p.m0.n0inv;
+    const uint8_t* sched = side ? p.sched1 : p.sched0;
+    uint32_t n[K];
+    M::load(n, mn);
+    const uint32_t* c = p.ct + ii * (size_t)(2 * L);
+    uint32_t acc[K];
+    {
+      uint32_t t[K];
+      M::load(acc, c);
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = 0;
+      if (M::lane_t() == 0) t[0] = 1;
+      M::put_sb(bsm, t);
+      M::mul_sb(acc, acc, bsm, n, n0inv);  // lo * R^-1
+      M::load(t, c + L);
+      uint32_t cy = M::group_add(acc, t, 0u);
+      if (__any_sync(IPCLB200_FULL_MASK, cy)) M::cond_sub_n(acc, n, cy);
+      M::load(t, mr3);
+      M::put_sb(bsm, t);
+      M::mul_sb(acc, acc, bsm, n, n0inv);  // ct * R mod n
+    }
+    const int nodd = sched[0];
+    M::store(tab, acc);
+    M::put_sb(bsm, acc);
+    M::mul_sb(acc, acc, bsm, n, n0inv);  // x^2
+    M::put_sb(bsm, acc);
+    M::load(acc, tab);
+    for (int i = 1; i < nodd; i++) {
+      M::mul_sb(acc, acc, bsm, n, n0inv);
+      M::store(tab + (size_t)i * L, acc);
+    }
+    M::load(acc, tab + (size_t)sched[1] * L);
+    M::put_sb(bsm, acc);
+    const uint8_t* op = sched + 2;
+#pragma unroll 1
+    for (uint32_t o = __ldg(op); o != 0xffu; o = __ldg(++op)) {
+      // the running value is the shared-memory operand; a window multiply
+      // loads the table entry into the register operand instead
+      if (o) M::load(acc, tab + (size_t)(o - 1) * L);
+      M::mul_sb(acc, acc, bsm, n, n0inv);
+      M::put_sb(bsm, acc);
+    }
+    {
+      uint32_t t[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = 0;
+      if (M::lane_t() == 0) t[0] = 1;
+      M::put_sb(bsm, t);
+      M::mul_sb(acc, acc, bsm, n, n0inv);
+      M::sub_n_if_ge(acc, n);
+    }
+    if (valid) M::store(p.x + (inst * 2 + side) * L, acc);
+  }
+}
+
 // --------------------------------------------------------------------------
 // K4s: the CRT-decrypt modexp with symmetric squarings (mont_sqr.cuh): the
 // squarings of the schedule (85 % of the products) go through MontSqr::sqr

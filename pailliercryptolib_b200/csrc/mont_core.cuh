@@ -232,6 +232,42 @@ struct Mont {
     finish(r, E, O, in_limb, n);
   }
 
+  // Same product with the multiplier's limbs read from shared memory (bsm:
+  // this group's L words, written by the caller, __syncwarp() done) instead of
+  // being broadcast out of K registers: frees K registers per lane, which is
+  // what lets the 32 x 2 layout keep 12 warps per SM.
+  __device__ __forceinline__ static void mul_sb(uint32_t (&r)[K],
+                                                const uint32_t (&a)[K],
+                                                const uint32_t* bsm,
+                                                const uint32_t (&n)[K],
+                                                uint32_t n0inv) {
+    uint32_t E[K + 1], O[K + 1];
+#pragma unroll
+    for (int j = 0; j <= K; j++) {
+      E[j] = 0;
+      O[j] = 0;
+    }
+    uint32_t in_limb = 0;
+#pragma unroll 1
+    for (int i = 0; i < L; i += 16) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const uint32_t b0 = bsm[i + j], b1 = bsm[i + j + 1];
+        in_limb = row(E, O, a, n, b0, in_limb, n0inv);
+        in_limb = row(O, E, a, n, b1, in_limb, n0inv);
+      }
+    }
+    finish(r, E, O, in_limb, n);
+  }
+  // this lane's K limbs -> the group's shared-memory operand
+  __device__ __forceinline__ static void put_sb(uint32_t* bsm, const uint32_t (&x)[K]) {
+    __syncwarp();
+    uint4* d = reinterpret_cast<uint4*>(bsm + lane_t() * K);
+#pragma unroll
+    for (int j = 0; j < K; j += 4) d[j / 4] = make_uint4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    __syncwarp();
+  }
+
   // Assemble the two arrays into K limbs per lane, resolve the cross-lane
   // carries and bring the value back below R.
   __device__ __forceinline__ static void finish(uint32_t (&r)[K],

@@ -72,6 +72,11 @@ if ok:
            if int.from_bytes(x[i, s_].tobytes(), "little") != pow(cts[i], (p, q)[s_] - 1, (p, q)[s_] ** 2)]
     os.environ["IPCLB200_DECRYPT"] = "int"
     x0 = sk.crt_residues(ct)
+    for extra in ("k32s", "k32s2"):
+        os.environ["IPCLB200_DECRYPT"] = extra
+        same = bool(np.array_equal(sk.crt_residues(ct), x0))
+        print("residues %s equal to the int kernel: %s" % (extra, same), flush=True)
+        ok = ok and same
     print("residues: %d wrong of 600 vs pow(); equal to the int kernel on all %d: %s" % (
         len(bad), count, bool(np.array_equal(x, x0))), flush=True)
     ok = ok and not bad and np.array_equal(x, x0)
@@ -87,7 +92,7 @@ if ok:
     d_ct = torch.empty((B, 128), dtype=torch.int32, device=dev)
     d_dt = torch.empty((B, 64), dtype=torch.int32, device=dev)
     pk.encrypt_dev(d_pt.data_ptr(), 64, d_r.data_ptr(), 32, B, d_ct.data_ptr(), st)
-    for mode in ("int", MODE, "k32"):
+    for mode in ("int", MODE, "k32", "k32s", "k32s2"):
         os.environ["IPCLB200_DECRYPT"] = mode
         ms = []
         for rep in range(4):
