@@ -180,6 +180,10 @@ int ipclb200_class_words(int words);
  * measure.  Also returns the kernel-launch count since init (for bench.py's
  * gpu_launches). */
 int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz);
+/* the same microbenchmark as a back-to-back train of launches lasting about
+ * `seconds`: the SUSTAINED integer rate, the denominator for a kernel that
+ * runs for hundreds of milliseconds (int_peak is the burst figure) */
+int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s);
 uint64_t ipclb200_launch_count(void);
 
 /* Pipe-overlap probe (profiles/r01_pipe_overlap.md): time of a fixed number of

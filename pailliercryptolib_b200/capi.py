@@ -35,7 +35,7 @@ EXPORTS = [
     "ipclb200_pipe_mix", "ipclb200_stream", "ipclb200_dev_alloc",
     "ipclb200_dev_free", "ipclb200_dev_upload", "ipclb200_dev_download",
     "ipclb200_dev_copy", "ipclb200_sync", "ipclb200_class_words",
-    "ipclb200_debug_montsqr",
+    "ipclb200_debug_montsqr", "ipclb200_int_peak_sustained",
 ]
 
 
@@ -94,6 +94,12 @@ def int_peak():
     macs, mhz = ctypes.c_double(), ctypes.c_double()
     _check(lib().ipclb200_int_peak(ctypes.byref(macs), ctypes.byref(mhz)))
     return macs.value, mhz.value
+
+
+def int_peak_sustained(seconds=0.3):
+    macs = ctypes.c_double()
+    _check(lib().ipclb200_int_peak_sustained(ctypes.c_double(seconds), ctypes.byref(macs)))
+    return macs.value
 
 
 def debug_montsqr(a, mod):

@@ -1745,6 +1745,43 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
   return 0;
 }
 
+int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s) {
+  if (!mac32_per_s || seconds <= 0 || seconds > 20)
+    return fail(IPCLB200_ERR_BAD_ARG, "int_peak_sustained: bad argument");
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  TRY(ensure_init_locked());
+  cudaStream_t s = g_ctx.stream;
+  const int threads = 256, blocks = g_ctx.sms * 8;
+  uint32_t* d_out;
+  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  // one launch is ~1 ms: time a back-to-back train of them.
+  // IPCLB200_PEAK_PATTERN=row: distinct multiplicand registers, as in a CIOS row
+  const char* pat = getenv("IPCLB200_PEAK_PATTERN");
+  const bool rowpat = pat && !strcmp(pat, "row");
+  int_peak_kernel<<<blocks, threads, 0, s>>>(d_out, 3u, 5u);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const int launches = (int)(seconds * 1000.0) + 1;
+  CUDA_TRY(cudaEventRecord(a, s));
+  for (int i = 0; i < launches; i++) {
+    if (rowpat)
+      int_peak_row_kernel<<<blocks, threads, 0, s>>>(d_out, 3u + i, 5u);
+    else
+      int_peak_kernel<<<blocks, threads, 0, s>>>(d_out, 3u + i, 5u);
+  }
+  CUDA_TRY(cudaEventRecord(b, s));
+  CUDA_TRY(cudaEventSynchronize(b));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+  g_ctx.launches += launches + 1;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *mac32_per_s = (double)threads * blocks * kPeakIters * 16.0 * launches / (ms * 1e-3);
+  return 0;
+}
+
 int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
                            uint32_t* out_sqr, uint32_t* out_mul) {
   if (!a || !mod || !out_sqr || !out_mul)

@@ -1425,6 +1425,48 @@ __global__ void int_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
 }
 
 
+// The same peak measurement with the operand pattern of a real CIOS row: 16
+// different multiplicand registers per chain (a[j] * b, n[j] * q) instead of
+// one register pair reused by every multiply.
+__global__ void int_peak_row_kernel(uint32_t* out, uint32_t a0, uint32_t b0) {
+  uint32_t e[17], o[17], a[16], n[16];
+#pragma unroll
+  for (int i = 0; i < 17; i++) {
+    e[i] = threadIdx.x + i;
+    o[i] = threadIdx.x * 3 + i;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    a[i] = a0 * (i + 1) + threadIdx.x;
+    n[i] = b0 * (i + 3) ^ threadIdx.x;
+  }
+  uint32_t b = b0, q = a0 ^ 0x5555u;
+  for (int it = 0; it < kPeakIters; it++) {
+    mad_lo_cc(e[0], a[0], b, e[0]);
+    madc_hi_cc(e[1], a[0], b, e[1]);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+      madc_lo_cc(e[i], a[i], b, e[i]);
+      madc_hi_cc(e[i + 1], a[i], b, e[i + 1]);
+    }
+    addc(e[16], e[16], 0);
+    mad_lo_cc(o[0], n[1], q, o[0]);
+    madc_hi_cc(o[1], n[1], q, o[1]);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+      madc_lo_cc(o[i], n[i + 1 < 16 ? i + 1 : 15], q, o[i]);
+      madc_hi_cc(o[i + 1], n[i + 1 < 16 ? i + 1 : 15], q, o[i + 1]);
+    }
+    addc(o[16], o[16], 0);
+    b += e[16];
+    q ^= o[16];
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 17; i++) s ^= e[i] ^ o[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // --------------------------------------------------------------------------
 // Pipe-overlap probe: do IMAD.WIDE (integer multiply pipe) and DFMA (FP64
 // pipe) run at the same time on one SM sub-partition?  mode 0: every warp runs
