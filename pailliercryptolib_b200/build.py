@@ -22,6 +22,11 @@ ORACLE_LIB = os.path.join(ORACLE, "_build", "libpaillier_oracle.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
     "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared",
+    # one translation unit with ~80 kernel instantiations: let the optimiser
+    # work on them in parallel (3 min -> 1.5 min); a fixed split keeps the
+    # generated code independent of the build machine's core count
+    # (measured with this split: 368.5 k pairs/s, unsplit 369.2 k)
+    "--split-compile", "8",
 ]
 
 
