@@ -532,6 +532,8 @@ struct ipclb200_pubkey {
   mutable uint32_t* d_comb = nullptr;
   mutable int comb_w = 0;
   mutable int comb_windows = 0;
+  mutable size_t enc_total = 0;  // elements encrypted with this key so far
+  mutable bool comb_full = false;  // the table was built at the budget width
   uint8_t* d_sched_n = nullptr;  // sliding-window schedule of the exponent n
   ~ipclb200_pubkey() {
     if (d_const) cudaFree(d_const);
@@ -685,9 +687,13 @@ int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
   return 0;
 }
 
-int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
+// small = true: the starter table (8-bit windows, 17 MB at a 2048-bit key);
+// false: the widest table the budget allows
+int build_comb(const ipclb200_pubkey* pk, int bits, bool small, cudaStream_t s) {
   const int L = pk->L;
-  if (pk->d_comb && pk->comb_windows * pk->comb_w >= bits) return 0;
+  constexpr int kStarterWindow = 8;
+  if (pk->d_comb && pk->comb_windows * pk->comb_w >= bits && (small || pk->comb_full))
+    return 0;
   // Widest window (<= 16 bits) whose table fits the budget.  B200 has 180 GB of
   // HBM and the kernel needs one 4L-byte entry per window and element, so the
   // table can be large: 1024-bit r at a 2048-bit key, w = 16 -> 64 windows x
@@ -701,6 +707,7 @@ int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
     return (size_t)((bits + ww - 1) / ww) * ((size_t)L << ww);
   };
   while (w > 4 && table_words(w) * 4 > (budget_mb << 20)) w--;
+  if (small && w > kStarterWindow) w = kStarterWindow;
   if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
     int v = atoi(cw);
     if (v >= 1 && v <= 16) w = v;
@@ -751,6 +758,7 @@ int build_comb(const ipclb200_pubkey* pk, int bits, cudaStream_t s) {
   CUDA_TRY(cudaStreamSynchronize(s));  // one-off; later users may be on other streams
   pk->comb_w = w;
   pk->comb_windows = windows;
+  pk->comb_full = !small;
   return 0;
 }
 
@@ -780,7 +788,16 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
     // DJN: fixed-base comb (built on first use, ~20 ms and up to 160 MB per
     // key; IPCLB200_NO_COMB=1 keeps the generic windowed path instead)
     if (!(no_comb && no_comb[0] == '1')) {
-      TRY(build_comb(pk, r_bits > pk->rand_bits ? r_bits : pk->rand_bits, s));
+      // a key starts with a small table (8-bit windows: 17 MB and ~130 products
+      // per encryption at a 2048-bit key) and moves to the widest one the budget
+      // allows (16-bit windows, 2.1 GB, 66 products) once it has encrypted
+      // IPCLB200_COMB_UPGRADE (default 8192) elements: a key that is used a few
+      // times does not pay for 2 GB of HBM
+      size_t upgrade_at = 8192;
+      if (const char* e = getenv("IPCLB200_COMB_UPGRADE")) upgrade_at = strtoul(e, nullptr, 10);
+      pk->enc_total += count;
+      TRY(build_comb(pk, r_bits > pk->rand_bits ? r_bits : pk->rand_bits,
+                     pk->enc_total < upgrade_at, s));
       p.mode = 1;
       p.comb = pk->d_comb;
       p.comb_w = pk->comb_w;

@@ -253,6 +253,28 @@ def test_encrypt_decrypt_batch_vs_oracle(capi, oracle, keys, bits, layout):
     assert np.array_equal(c_w, oracle.encrypt(nl, hsl, pt[:70], r_wide))
 
 
+def test_comb_table_upgrade_keeps_results(capi, oracle, keys, monkeypatch):
+    """a DJN key starts with the small fixed-base table (8-bit windows) and moves
+    to the wide one after IPCLB200_COMB_UPGRADE elements: same ciphertexts from
+    both, equal to the oracle"""
+    k = keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    rng = np.random.default_rng(808)
+    pt = random_limbs(rng, 300, 64, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, 300, 32)
+    nl, hsl = to_limbs(n, 64), to_limbs(k["hs"], 128)
+    monkeypatch.setenv("IPCLB200_COMB_UPGRADE", "500")
+    pk = capi.PubKey(nl, hsl, 1024)
+    c_small = pk.encrypt(pt, r)     # 300 elements so far: starter table
+    c_wide = pk.encrypt(pt, r)      # 600: upgraded
+    c_again = pk.encrypt(pt, r)
+    want = oracle.encrypt(nl, hsl, pt, r)
+    assert np.array_equal(c_small, want)
+    assert np.array_equal(c_wide, want)
+    assert np.array_equal(c_again, want)
+
+
 def test_homomorphic_properties_large_batch(capi, keys):
     """size-independent checks at a batch the oracle would need minutes for:
     dec(enc(a) * enc(b)) = a + b mod n, dec(enc(a)^k) = a*k mod n."""
