@@ -50,18 +50,37 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
+def _cuda_sources():
+    srcs = [os.path.join(CSRC, f) for f in
+            ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "mont_hensel.cuh",
+             "hostbn.hpp")]
+    exp = os.path.join(CSRC, "experiments")
+    srcs += sorted(os.path.join(exp, f) for f in os.listdir(exp))
+    srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))
+    return srcs
+
+
+def experiments_enabled():
+    """The kernels that measured slower (csrc/experiments/) are compiled only on
+    request: IPCLB200_EXPERIMENTS=1 in the environment or build.py --experiments."""
+    return os.environ.get("IPCLB200_EXPERIMENTS", "0") == "1"
+
+
 def build_cuda(force=False, verbose=False):
     """libipcl_b200.so: kernels + C ABI (nvcc, sm_100a only)."""
-    srcs = [os.path.join(CSRC, f) for f in
-            ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "mont_fp64.cuh",
-             "mont_sqr.cuh", "mont_tile.cuh", "hostbn.hpp")]
-    srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))
-    if not force and _newer(CUDA_LIB, srcs):
+    srcs = _cuda_sources()
+    stamp = os.path.join(LIBDIR, ".experiments")
+    want = "1" if experiments_enabled() else "0"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else None
+    if not force and have == want and _newer(CUDA_LIB, srcs):
         return CUDA_LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (
+        ["-DIPCLB200_EXPERIMENTS"] if want == "1" else []) + [
         "-o", CUDA_LIB, os.path.join(CSRC, "ipcl_b200.cu")]
     out = _run(cmd)
+    with open(stamp, "w") as f:
+        f.write(want)
     if verbose:
         print(out)
     return CUDA_LIB
@@ -151,6 +170,8 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--experiments" in sys.argv:
+        os.environ["IPCLB200_EXPERIMENTS"] = "1"
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("built:", CUDA_LIB, IPCL_LIB if os.path.exists(IPCL_LIB) else "",
           ORACLE_LIB)

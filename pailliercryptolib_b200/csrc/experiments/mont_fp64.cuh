@@ -28,7 +28,7 @@
 #pragma once
 #include <cstdint>
 
-#include "mont_core.cuh"
+#include "../mont_core.cuh"
 
 namespace ipclb200 {
 

@@ -19,6 +19,9 @@
 #include "../../include/ipcl_b200.h"
 #include "hostbn.hpp"
 #include "kernels.cuh"
+#ifdef IPCLB200_EXPERIMENTS
+#include "experiments/kernels_exp.cuh"
+#endif
 
 using namespace ipclb200;
 using hbn::Limbs;
@@ -148,6 +151,7 @@ int pick_window(int ebits) {
 
 constexpr int kSchedWindow = 5;  // 16 odd powers per table
 
+#ifdef IPCLB200_EXPERIMENTS
 // byte code for decrypt_tile_kernel (opcodes: kernels.cuh) from a
 // sliding-window schedule: reduce the ciphertext, enter Montgomery form, build
 // the odd powers x, x^3, ... with x^2 parked in an extra slot, run the
@@ -170,6 +174,8 @@ std::vector<uint8_t> build_tile_program(const std::vector<uint8_t>& sched) {
   p.push_back(0xc2);
   return p;
 }
+
+#endif
 
 // left-to-right sliding-window schedule for a fixed exponent (format: see
 // modexp_sched_core in kernels.cuh).  e > 0.
@@ -203,6 +209,46 @@ std::vector<uint8_t> build_schedule(const Limbs& e, int w) {
   return s;
 }
 
+// decrypt_hensel_kernel's schedule: the byte schedule of build_schedule as 32-bit
+// words [nodd, first, (run << 8 | entry)..., (run << 8 | 0xff)]: `run` squarings,
+// then a multiply by odd power `entry` (0xff: none, end)
+std::vector<uint32_t> hensel_schedule(const std::vector<uint8_t>& sched) {
+  std::vector<uint32_t> out = {sched[0], sched[1]};
+  uint32_t run = 0;
+  for (size_t i = 2; sched[i] != 0xff; i++) {
+    if (sched[i] == 0) {
+      run++;
+    } else {
+      out.push_back((run << 8) | (uint32_t)(sched[i] - 1));
+      run = 0;
+    }
+  }
+  out.push_back((run << 8) | 0xffu);
+  return out;
+}
+
+// per-side constants of the two-digit decrypt (10*pl words):
+//   p | pairs (k0_j, kw_j) of R^(j+1) mod p^2 in Montgomery form, j = 0..3 | -hp mod p
+// A pair (x0, w) stands for x0 - w*p mod p^2 (mont_hensel.cuh).
+void hensel_side_block(const Limbs& p, const Limbs& psq, const Limbs& hp, int pl,
+                       uint32_t* out) {
+  hbn::to_words(p, out, pl);
+  const Limbs R = hbn::pow2(32u * (unsigned)pl);
+  Limbs t = hbn::mod(R, psq);  // R^1
+  for (int j = 0; j < 4; j++) {
+    t = hbn::mod(hbn::mul(t, R), psq);  // R^(j+2) = R^(j+1) in Montgomery form
+    Limbs hi, lo;
+    hbn::divmod(t, p, &hi, &lo);
+    Limbs wneg = hbn::mod(hi, p);
+    Limbs w = hbn::is_zero(wneg) ? wneg : hbn::sub(p, wneg);
+    hbn::to_words(lo, out + (size_t)(1 + 2 * j) * pl, pl);
+    hbn::to_words(w, out + (size_t)(2 + 2 * j) * pl, pl);
+  }
+  Limbs nhp = hbn::is_zero(hp) ? hp : hbn::sub(p, hp);
+  hbn::to_words(nhp, out + (size_t)9 * pl, pl);
+}
+
+#ifdef IPCLB200_EXPERIMENTS
 // FP64 role (mont_fp64.cuh): the 64-word class (p^2 of a 2048-bit key) as 96
 // limbs of 22 bits over 4 lanes
 constexpr int kFpWords = 64;
@@ -220,6 +266,8 @@ void fp_limbs(const Limbs& x, double* out, int L) {
     out[g] = (double)((v >> sh) & kFpMask);
   }
 }
+
+#endif
 
 // ---------------------------------------------------------------------------
 // per-modulus constants
@@ -560,6 +608,14 @@ struct ipclb200_privkey {
   uint8_t* d_sched = nullptr;
   const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr,
                 *d_sched_lambda = nullptr;
+  // two-digit (Hensel) decrypt, mont_hensel.cuh: per side p | K_0..K_3 | -hp
+  // (10*pl words) and the run-length schedules; hensel_ok: p and q fill their
+  // pl words and pl is a layout of decrypt_hensel_kernel
+  uint32_t* d_hensel = nullptr;
+  const uint32_t *d_hblk_p = nullptr, *d_hblk_q = nullptr, *d_hsched_p = nullptr,
+                 *d_hsched_q = nullptr;
+  bool hensel_ok = false;
+#ifdef IPCLB200_EXPERIMENTS
   // byte-code programs of the thread-per-integer kernel and -N^-1 mod 2^256
   const uint8_t *d_prog_p = nullptr, *d_prog_q = nullptr;
   uint32_t ninv_p[8] = {}, ninv_q[8] = {};
@@ -568,10 +624,14 @@ struct ipclb200_privkey {
   double* d_fp = nullptr;
   FpModConst fp0{}, fp1{};
   bool fp_ok = false;
+#endif
   ~ipclb200_privkey() {
     if (d_const) cudaFree(d_const);
     if (d_sched) cudaFree(d_sched);
+    if (d_hensel) cudaFree(d_hensel);
+#ifdef IPCLB200_EXPERIMENTS
     if (d_fp) cudaFree(d_fp);
+#endif
   }
 };
 
@@ -837,6 +897,76 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   return 0;
 }
 
+// CRT decrypt in two-digit arithmetic (decrypt_hensel_kernel + crt_combine_kernel).
+// d_x: count x 2*pl words (mp | mq per ciphertext).
+int decrypt_hensel_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
+                        size_t count, uint32_t* d_pt, uint32_t* d_x,
+                        cudaStream_t s) {
+  const int pl = sk->pl;
+  DecryptHenselParams p{};
+  p.ct = d_ct;
+  p.s0.blk = sk->d_hblk_p;
+  p.s0.sched = sk->d_hsched_p;
+  p.s0.n0inv = sk->p_n0inv;
+  p.s1.blk = sk->d_hblk_q;
+  p.s1.sched = sk->d_hsched_q;
+  p.s1.n0inv = sk->q_n0inv;
+  p.mpq = d_x;
+  p.count = count;
+  p.table_entries = 1 << (kSchedWindow - 1);
+  // warps per SM: IPCLB200_HENSEL_BLOCKS blocks of 128 threads (default 3)
+  int want_blocks = 3;
+  if (const char* e = getenv("IPCLB200_HENSEL_BLOCKS")) want_blocks = atoi(e);
+  if (want_blocks < 1 || want_blocks > 4) want_blocks = 3;
+#define FH(K_, T_, MINB_, ROWS_)                                                        \
+  {                                                                                \
+    auto kern = decrypt_hensel_kernel<K_, T_, MINB_, ROWS_>;                          \
+    constexpr size_t smem = hensel_smem_bytes<K_, T_>(kBlockThreads);              \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                     \
+    int per_sm = 0;                                                                \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,          \
+                                                           kBlockThreads, smem));  \
+    if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "hensel kernel does not fit an SM"); \
+    if (per_sm > want_blocks) per_sm = want_blocks;                                \
+    const size_t gpb = kBlockThreads / T_;                                         \
+    const size_t chunks = 2 * ((count + (32 / T_) - 1) / (32 / T_));               \
+    const size_t need = (chunks + 3) / 4;                                          \
+    const size_t cap = (size_t)per_sm * g_ctx.sms;                                 \
+    const int grid = (int)(need < cap ? need : cap);                               \
+    TRY(table_ws_with_counter(s, (size_t)grid * gpb * 2 * pl * p.table_entries,    \
+                              &p.table_ws, &p.work_counter));                      \
+    kern<<<grid, kBlockThreads, smem, s>>>(p);                                     \
+  }
+  int rows = 8;
+  if (const char* e = getenv("IPCLB200_HENSEL_ROWS")) rows = atoi(e);
+  switch (pl) {
+    case 16: FH(8, 2, 3, 8) break;
+    case 32:
+      if (rows == 4) FH(16, 2, 3, 4) else if (rows == 16) FH(16, 2, 3, 16) else FH(16, 2, 3, 8)
+      break;
+    case 48: FH(24, 2, 2, 8) break;
+    case 64: FH(16, 4, 3, 8) break;
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel: unsupported prime width");
+  }
+#undef FH
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  CrtCombineParams f{};
+  f.mpq = d_x;
+  f.p = sk->d_p;
+  f.q = sk->d_q;
+  f.pinvR = sk->d_pinvR;
+  f.q_n0inv = sk->q_n0inv;
+  f.pl = pl;
+  f.pt = d_pt;
+  f.count = count;
+  crt_combine_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
+  g_ctx.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
                      size_t count, int use_crt, uint32_t* d_pt,
                      uint32_t* d_x /* count x 4*pl words scratch */,
@@ -847,6 +977,11 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
   // key: only 8 warps/SM fit its shared-memory columns and it issues 2.7
   // instructions per multiply); it stays opt-in
   const char* force = getenv("IPCLB200_DECRYPT");
+  // default: two-digit (Hensel) arithmetic, half the multiplies of the generic
+  // kernel; IPCLB200_DECRYPT=int keeps the full-width kernel
+  if (use_crt && sk->hensel_ok && (!force || !strcmp(force, "hensel")))
+    return decrypt_hensel_impl(sk, d_ct, count, d_pt, d_x, s);
+#ifdef IPCLB200_EXPERIMENTS
   const bool tile = force && !strcmp(force, "tile");
   if (use_crt && tile && (sk->L == 32 || sk->L == 48 || sk->L == 64)) {
     const int L = sk->L;
@@ -906,7 +1041,9 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
     g_ctx.launches += 2;
     CUDA_TRY(cudaGetLastError());
-  } else if (use_crt) {
+  } else
+#endif
+  if (use_crt) {
     const int L = sk->L;
     DecryptCrtParams p{};
     p.ct = d_ct;
@@ -920,6 +1057,7 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     // which pipes: "int" = integer kernel only, "fp" = FP64 kernel only,
     // "dual" = both roles in one kernel, "dual2" = two kernels on two streams
     // sharing the work counter.  FP64 needs the 64-word class (2048-bit key).
+#ifdef IPCLB200_EXPERIMENTS
     const char* mode = force ? force : "int";
     const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
                want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
@@ -1096,7 +1234,9 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
         g_ctx.launches += 2;
       }
       CUDA_TRY(cudaGetLastError());
-    } else {
+    } else
+#endif
+    {
       int grid = 0;
 #define F(K_, T_)                                                          \
   {                                                                        \
@@ -1540,7 +1680,11 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   {
     std::vector<uint8_t> sp = build_schedule(pm1, kSchedWindow);
     std::vector<uint8_t> sq = build_schedule(qm1, kSchedWindow);
+#ifdef IPCLB200_EXPERIMENTS
     std::vector<uint8_t> pp = build_tile_program(sp), pq = build_tile_program(sq);
+#else
+    std::vector<uint8_t> pp, pq;
+#endif
     std::vector<uint8_t> sl = build_schedule(lam, kSchedWindow);
     std::vector<uint8_t> both(sp);
     both.insert(both.end(), sq.begin(), sq.end());
@@ -1551,17 +1695,39 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
     CUDA_TRY(cudaMemcpy(sk->d_sched, both.data(), both.size(), cudaMemcpyHostToDevice));
     sk->d_sched_p = sk->d_sched;
     sk->d_sched_q = sk->d_sched + sp.size();
+    sk->d_sched_lambda = sk->d_sched_q + sq.size() + pp.size() + pq.size();
+#ifdef IPCLB200_EXPERIMENTS
     sk->d_prog_p = sk->d_sched_q + sq.size();
     sk->d_prog_q = sk->d_prog_p + pp.size();
-    sk->d_sched_lambda = sk->d_prog_q + pq.size();
     sk->tile_slots = sp[0] + 1;
     Limbs two256 = hbn::pow2(256), inv;
     hbn::modinv(hbn::mod(psq, two256), two256, &inv);
     hbn::to_words(hbn::sub(two256, inv), sk->ninv_p, 8);
     hbn::modinv(hbn::mod(qsq, two256), two256, &inv);
     hbn::to_words(hbn::sub(two256, inv), sk->ninv_q, 8);
+#endif
+    // two-digit decrypt: needs primes that fill their words (so that a digit
+    // < R is < 2p) and a prime width decrypt_hensel_kernel is instantiated for
+    sk->hensel_ok = hbn::bitlen(p) == 32 * pl && hbn::bitlen(q) == 32 * pl &&
+                    (pl == 16 || pl == 32 || pl == 48 || pl == 64);
+    if (sk->hensel_ok) {
+      std::vector<uint32_t> hs_p = hensel_schedule(sp), hs_q = hensel_schedule(sq);
+      std::vector<uint32_t> blk(20 * (size_t)pl + hs_p.size() + hs_q.size(), 0u);
+      hensel_side_block(p, psq, hp, pl, blk.data());
+      hensel_side_block(q, qsq, hq, pl, blk.data() + 10 * (size_t)pl);
+      std::copy(hs_p.begin(), hs_p.end(), blk.begin() + 20 * (size_t)pl);
+      std::copy(hs_q.begin(), hs_q.end(), blk.begin() + 20 * (size_t)pl + hs_p.size());
+      CUDA_TRY(cudaMalloc(&sk->d_hensel, blk.size() * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemcpy(sk->d_hensel, blk.data(), blk.size() * sizeof(uint32_t),
+                          cudaMemcpyHostToDevice));
+      sk->d_hblk_p = sk->d_hensel;
+      sk->d_hblk_q = sk->d_hensel + 10 * (size_t)pl;
+      sk->d_hsched_p = sk->d_hensel + 20 * (size_t)pl;
+      sk->d_hsched_q = sk->d_hsched_p + hs_p.size();
+    }
   }
   sk->lambda_bits = hbn::bitlen(lam);
+#ifdef IPCLB200_EXPERIMENTS
   if (sk->L == kFpWords) {
     // radix-2^22 constants of the FP64 role: n and R^3 mod n, R = 2^(22*96)
     constexpr int FL = kFpLimbs;
@@ -1588,6 +1754,7 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
     sk->fp1.n0inv = hbn::neg_inv32(qsq[0]) & kFpMask;
     sk->fp_ok = true;
   }
+#endif
   *out = sk.release();
   return 0;
 }
@@ -1801,6 +1968,9 @@ int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s) {
 
 int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
                            uint32_t* out_sqr, uint32_t* out_mul) {
+#ifndef IPCLB200_EXPERIMENTS
+  return fail(IPCLB200_ERR_UNSUPPORTED, "debug_montsqr: built without -DIPCLB200_EXPERIMENTS");
+#else
   if (!a || !mod || !out_sqr || !out_mul)
     return fail(IPCLB200_ERR_BAD_ARG, "debug_montsqr: null pointer");
   if (count == 0) return 0;
@@ -1844,9 +2014,13 @@ int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
   CUDA_TRY(cudaMemcpyAsync(out_mul, d_m, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return 0;
+#endif
 }
 
 int ipclb200_pipe_mix(int mode, double* ms_out) {
+#ifndef IPCLB200_EXPERIMENTS
+  return fail(IPCLB200_ERR_UNSUPPORTED, "pipe_mix: built without -DIPCLB200_EXPERIMENTS");
+#else
   if (mode < 0 || mode > 8 || !ms_out)
     return fail(IPCLB200_ERR_BAD_ARG, "pipe_mix: bad argument");
   std::lock_guard<std::mutex> lk(g_ctx.mu);
@@ -1873,6 +2047,7 @@ int ipclb200_pipe_mix(int mode, double* ms_out) {
   cudaEventDestroy(b);
   *ms_out = best;
   return 0;
+#endif
 }
 
 }  // extern "C"

@@ -1,0 +1,143 @@
+"""GPU parity of the two-digit (Hensel) CRT decrypt -- decrypt_hensel_kernel,
+pailliercryptolib_b200/csrc/mont_hensel.cuh -- through the C ABI: against the
+full-width kernel (IPCLB200_DECRYPT=int), against Python pow() restating
+ipcl/pri_key.cpp:114-167, and against the oracle at the full batch size."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pailliercryptolib_b200.limbs import (batch_from_limbs, batch_to_limbs,
+                                          random_limbs, to_limbs)
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden import dec_crt  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def all_keys(keys):
+    from conftest import load_golden
+    extra = {name: {k: int(v, 16) for k, v in d.items()}
+             for name, d in load_golden("keys_extra.json").items()}
+    return {**keys, **extra}
+
+
+def _ciphertexts(rng, p, q, count):
+    """valid ciphertexts (units mod n^2): random residues, the edge values 1,
+    n+1, n^2-1, and unreduced inputs >= n^2 that fill all 4*pl words"""
+    n = p * q
+    nsq = n * n
+    words = 4 * ((p.bit_length() + 31) // 32)
+    top = 1 << (32 * words)
+    cts = []
+    while len(cts) < count:
+        c = int.from_bytes(rng.bytes(words * 4), "little") % nsq
+        if c % p and c % q:
+            cts.append(c)
+    cts[:3] = [1, n + 1, nsq - 1]
+    k = (top - 1) // nsq
+    cts[3] = cts[10] + (k - 1) * nsq if k > 1 else cts[10]
+    cts[4] = top - 1 if (top - 1) % p and (top - 1) % q else cts[11]
+    return cts, words
+
+
+@pytest.mark.parametrize("name", ["1024", "2048", "3072", "4096", "2048_low", "2048_high"])
+def test_hensel_decrypt_matches_full_width_and_pow(capi, all_keys, name, monkeypatch):
+    k = all_keys[name]
+    p, q = sorted((k["p"], k["q"]))
+    pl = (p.bit_length() + 31) // 32
+    rng = np.random.default_rng(sum(map(ord, name)))
+    count = 700 if pl <= 32 else 300
+    cts, words = _ciphertexts(rng, p, q, count)
+    ct = batch_to_limbs(cts, words)
+    sk = capi.PrivKey(to_limbs(p, pl), to_limbs(q, pl))
+    monkeypatch.delenv("IPCLB200_DECRYPT", raising=False)
+    got = sk.decrypt(ct)
+    monkeypatch.setenv("IPCLB200_DECRYPT", "int")
+    base = sk.decrypt(ct)
+    monkeypatch.delenv("IPCLB200_DECRYPT")
+    assert np.array_equal(got, base)
+    vals = batch_from_limbs(got)
+    for i in list(range(12)) + [count - 1]:
+        assert vals[i] == dec_crt(p, q, cts[i]), (name, i)
+    assert vals[0] == 0 and vals[1] == 1
+
+
+@pytest.mark.parametrize("count", [1, 5, 16, 17, 31, 100])
+def test_hensel_ragged_small_batches(capi, all_keys, count, monkeypatch):
+    k = all_keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    rng = np.random.default_rng(count)
+    pk = capi.PubKey(to_limbs(n, 64), to_limbs(k["hs"], 128), 1024)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    pt = random_limbs(rng, count, 64, top_mask=0x3FFFFFFF)
+    ct = pk.encrypt(pt, random_limbs(rng, count, 32))
+    monkeypatch.delenv("IPCLB200_DECRYPT", raising=False)
+    assert np.array_equal(sk.decrypt(ct), pt)
+
+
+@pytest.mark.parametrize("rows", ["4", "16"])
+def test_hensel_row_unroll_variants(capi, all_keys, rows, monkeypatch):
+    k = all_keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    rng = np.random.default_rng(int(rows))
+    cts, words = _ciphertexts(rng, p, q, 400)
+    ct = batch_to_limbs(cts, words)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    monkeypatch.delenv("IPCLB200_DECRYPT", raising=False)
+    base = sk.decrypt(ct)
+    monkeypatch.setenv("IPCLB200_HENSEL_ROWS", rows)
+    assert np.array_equal(sk.decrypt(ct), base)
+    assert batch_from_limbs(base[:4]) == [dec_crt(p, q, c) for c in cts[:4]]
+
+
+def test_full_batch_65536_bit_exact_vs_oracle(capi, oracle, keys):
+    """BASELINE.json configs[1] at full size, every element compared bit for bit
+    with the oracle (AVX512-IFMA mb8 restatement, itself pinned to the ISO KAT
+    and to the scalar oracle in tests/test_oracle.py): 65536 ciphertexts from
+    the 16-bit comb table the bench times, 65536 plaintexts from the two-digit
+    decrypt."""
+    if not oracle.have_ifma():
+        pytest.skip("host without AVX512-IFMA: the scalar oracle needs minutes for 65536")
+    k = keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL, count = 64, 65536
+    rng = np.random.default_rng(20481)
+    pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, count, 32)
+    nl, hsl = to_limbs(n, NL), to_limbs(k["hs"], 2 * NL)
+    pk = capi.PubKey(nl, hsl, 1024)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    ct = pk.encrypt(pt, r)
+    ct2 = pk.encrypt(pt, r)  # second call: the upgraded (16-bit window) table
+    want_ct = oracle.encrypt_mb8(nl, hsl, pt, r)
+    assert np.array_equal(ct, want_ct)
+    assert np.array_equal(ct2, want_ct)
+    got = sk.decrypt(ct)
+    assert np.array_equal(got, oracle.decrypt_crt_mb8(to_limbs(p, 32), to_limbs(q, 32), ct))
+    assert np.array_equal(got, pt)
+
+
+def test_3072_bit_key_4096_elements_vs_oracle(capi, oracle, keys):
+    """BASELINE.json configs[3] key size, 4096 elements, every one compared with
+    the oracle (scalar for the 6144-bit encrypt, which mbx_exp_mb8 cannot do)"""
+    k = keys["3072"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL, count = 96, 4096
+    rng = np.random.default_rng(3072)
+    pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, count, 48)
+    nl, hsl = to_limbs(n, NL), to_limbs(k["hs"], 2 * NL)
+    pk = capi.PubKey(nl, hsl, 1536)
+    sk = capi.PrivKey(to_limbs(p, 48), to_limbs(q, 48))
+    ct = pk.encrypt(pt, r)
+    assert np.array_equal(ct, oracle.encrypt(nl, hsl, pt, r))
+    got = sk.decrypt(ct)
+    assert np.array_equal(got, pt)
+    assert np.array_equal(got, oracle.decrypt_crt(to_limbs(p, 48), to_limbs(q, 48), ct))

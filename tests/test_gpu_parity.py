@@ -2,6 +2,7 @@
 fixtures and the reference's ISO/IEC 18033-6 known-answer vectors.  Bit-exact:
 integer work, no tolerance."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -307,6 +308,12 @@ def test_int_peak_reports(capi):
     assert macs > 1e12 and mhz > 500
 
 
+needs_experiments = pytest.mark.skipif(
+    os.environ.get("IPCLB200_EXPERIMENTS", "0") != "1",
+    reason="libipcl_b200.so is built without -DIPCLB200_EXPERIMENTS (build.py --experiments)")
+
+
+@needs_experiments
 @pytest.mark.parametrize("bits", ["1024", "2048"])
 def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     """the opt-in thread-per-integer decrypt kernel (mont_tile.cuh) gives the
@@ -330,6 +337,7 @@ def test_decrypt_tile_kernel_matches(capi, keys, bits, monkeypatch):
     assert np.array_equal(alt, pt)
 
 
+@needs_experiments
 @pytest.mark.parametrize("sq_layout,mode", [("1", "sqr"), ("2", "sqr2")])
 def test_symmetric_squaring_kernel(capi, keys, monkeypatch, sq_layout, mode):
     """MontSqr::sqr / MontSqr2::sqr (mont_sqr.cuh, opt-in IPCLB200_DECRYPT=sqr|sqr2,
@@ -370,7 +378,6 @@ def test_symmetric_squaring_kernel(capi, keys, monkeypatch, sq_layout, mode):
 
 
 FP_CONFIGS = [
-    ("int", {}),
     ("fp", {"IPCLB200_FP_BLOCKS": "2"}),
     ("fp", {"IPCLB200_FP_BLOCKS": "3"}),
     ("dual", {"IPCLB200_FP_MASK": "4"}),
@@ -380,9 +387,22 @@ FP_CONFIGS = [
 ]
 
 
+def test_decrypt_full_width_residues_vs_pow(capi, keys, monkeypatch):
+    """the full-width kernel (IPCLB200_DECRYPT=int; the fallback of the two-digit
+    decrypt for primes that do not fill their words) leaves the canonical residues
+    ct^(p-1) mod p^2, ct^(q-1) mod q^2, incl. ciphertexts 0, 1, n^2-1 and multiples
+    of p and q^2"""
+    _residues_vs_pow(capi, keys, "int", {}, monkeypatch)
+
+
+@needs_experiments
 @pytest.mark.parametrize("mode,env", FP_CONFIGS,
                          ids=["-".join([m] + list(e.values())) for m, e in FP_CONFIGS])
 def test_decrypt_pipes_residues_vs_pow(capi, keys, mode, env, monkeypatch):
+    _residues_vs_pow(capi, keys, mode, env, monkeypatch)
+
+
+def _residues_vs_pow(capi, keys, mode, env, monkeypatch):
     """every pipe configuration of the CRT-decrypt modexp (integer pipe, FP64
     pipe, both in one kernel, both as two kernels sharing the work counter)
     leaves the canonical residues ct^(p-1) mod p^2, ct^(q-1) mod q^2 -- checked
