@@ -22,8 +22,10 @@
  * Host-pointer entry points copy in, compute and copy out synchronously.
  * *_dev entry points take device pointers on the current device plus a CUDA
  * stream (passed as void*) and only enqueue work.
- * All entry points are re-entrant; concurrent callers are serialised per
- * device inside the library (the reference's encrypt/decrypt are called
+ * All entry points are re-entrant and lock-free on the data path: every
+ * host-pointer call runs on its own stream with stream-ordered temporaries,
+ * every *_dev call allocates its intermediates on the caller's stream, so
+ * concurrent callers overlap (the reference's encrypt/decrypt are called
  * concurrently on one key, test/test_cryptography.cpp:45-57).
  */
 #ifndef IPCL_B200_H_
@@ -42,6 +44,7 @@ extern "C" {
 #define IPCLB200_ERR_CUDA (-3)         /* a CUDA runtime call failed           */
 #define IPCLB200_ERR_NO_DEVICE (-4)    /* no usable sm_100 device              */
 #define IPCLB200_ERR_UNSUPPORTED (-5)  /* width not supported by this entry    */
+#define IPCLB200_ERR_NCCL (-6)         /* NCCL missing or a NCCL call failed   */
 
 /* operand broadcast flags: the operand is ONE value used by every element
  * (what std::vector<BigNumber>(sz, x) expresses at ipcl/pub_key.cpp:53-54,
@@ -60,8 +63,20 @@ extern "C" {
  * (ipcl/utils/context.cpp:40-86).  device < 0 selects the current device (or
  * LOCAL_RANK when set).  Idempotent. */
 int ipclb200_init(int device);
+/* One process, several GPUs: host-pointer entry points and ipclb200_batch_*
+ * split every batch into contiguous blocks over devices 0..n_devices-1
+ * (n_devices <= 0: all visible devices); per-key constants and fixed-base
+ * tables are replicated per device on first use.  This is the slot of the
+ * reference's static prefix/suffix split of a batch between the CPU and the
+ * accelerator (ipcl/mod_exp.cpp:702-731).  Blocks smaller than 512 elements are
+ * not split off (IPCLB200_MIN_SHARD).  Call before the first batch. */
+int ipclb200_init_devices(int n_devices);
+int ipclb200_active_devices(void);
 void ipclb200_shutdown(void);
 int ipclb200_device_count(void);
+/* 1 if the library was built with -DIPCLB200_EXPERIMENTS (the kernels that
+ * measured slower: FP64 pipe, symmetric squarings, thread-per-integer) */
+int ipclb200_has_experiments(void);
 const char* ipclb200_last_error(void);
 const char* ipclb200_version(void);
 
@@ -111,6 +126,16 @@ typedef struct ipclb200_pubkey ipclb200_pubkey;
 int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs,
                            int rand_bits, ipclb200_pubkey** out);
 void ipclb200_pubkey_destroy(ipclb200_pubkey* pk);
+/* Fixed-base table policy of a DJN key (hs^r is computed from a comb table of
+ * hs, the same base for every element: ipcl/pub_key.cpp:53).  A key starts with
+ * a 17 MB table (8-bit windows) and, once it has encrypted `upgrade_after`
+ * elements (default 8192), gets the widest table below `max_table_mb` (default
+ * 4096; 16-bit windows = 2.1 GB at a 2048-bit key) built on a side stream --
+ * encryptions keep using the small table until the wide one is ready.  Wide
+ * tables of all keys on a device stay below IPCLB200_COMB_DEVICE_MB (64 GB).
+ * A negative argument keeps the current value. */
+int ipclb200_pubkey_set_table_policy(ipclb200_pubkey* pk, long max_table_mb,
+                                     long upgrade_after);
 
 /* ct[i] = ((n*pt[i] + 1) mod n^2) * obf[i] mod n^2,
  *   obf[i] = hs^r[i] mod n^2 (DJN) or r[i]^n mod n^2 (non-DJN).
@@ -154,8 +179,10 @@ int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
  * these for its device-resident CipherText.  The counterpart in the reference
  * is the buffer acquire/release of the QAT offload
  * (module/heqat/heqat/include/heqat/bnops.h:121-148).
- * All of them work on the library's own stream, ipclb200_stream(), which is
- * also the stream to hand to the *_dev entry points for work on these buffers:
+ * All of them work on the library's own stream of the primary device,
+ * ipclb200_stream(), which is also the stream to hand to the *_dev entry points
+ * for work on these buffers (the *_dev calls run on the device that owns their
+ * output pointer):
  * allocation, copies, kernels and frees are then ordered on that one stream.
  *   dev_alloc / dev_free : stream-ordered (cudaMallocAsync / cudaFreeAsync)
  *   dev_upload           : the host buffer may be reused on return
@@ -172,6 +199,50 @@ int ipclb200_dev_download(void* h, const void* d, size_t bytes);
 int ipclb200_dev_copy(void* d_dst, const void* d_src, size_t bytes);
 int ipclb200_sync(void);
 int ipclb200_class_words(int words);
+/* page-locked (pinned, portable) host memory: copies from/to it are DMA
+ * transfers that overlap across devices and with kernels */
+int ipclb200_host_alloc(size_t bytes, void** out);
+int ipclb200_host_free(void* p);
+
+/* ---- batches sharded over the active devices ---------------------------------
+ * count x words limbs in HBM, split into contiguous blocks over the devices of
+ * ipclb200_init_devices (one block on one device otherwise).  Every operation
+ * on a batch is enqueued on the library stream of each shard's device; nothing
+ * waits until batch_download / batch_sync.  Batches of equal count are sharded
+ * identically, so element i of every operand lives on the same device.
+ *   batch_upload / download : host buffer of count x h_words (h_words <= words,
+ *                             zero padded / truncated per element)
+ *   batch_scatter / gather  : from / to ONE contiguous device buffer on the
+ *                             first device, NCCL grouped send/recv over NVLink
+ *                             (the "trivial scatter/gather of independent
+ *                             ciphertexts"; NCCL is loaded on first use)
+ *   encrypt / decrypt / modmul / modexp _batch : the *_dev entry points per shard.
+ *     modmul_batch: b == NULL -> one shared factor h_b_shared (host, mod_words);
+ *     modexp_batch: exp == NULL -> one shared exponent h_exp_shared (host). */
+typedef struct ipclb200_batch ipclb200_batch;
+int ipclb200_batch_alloc(size_t count, int words, ipclb200_batch** out);
+void ipclb200_batch_free(ipclb200_batch* b);
+size_t ipclb200_batch_count(const ipclb200_batch* b);
+int ipclb200_batch_words(const ipclb200_batch* b);
+int ipclb200_batch_num_shards(const ipclb200_batch* b);
+int ipclb200_batch_shard(const ipclb200_batch* b, int shard, int* device, void** d_ptr,
+                         size_t* begin, size_t* count, void** stream);
+int ipclb200_batch_upload(ipclb200_batch* b, const uint32_t* h, int h_words);
+int ipclb200_batch_download(const ipclb200_batch* b, uint32_t* h, int h_words);
+int ipclb200_batch_sync(const ipclb200_batch* b);
+int ipclb200_batch_scatter(ipclb200_batch* b, const uint32_t* d_src);
+int ipclb200_batch_gather(const ipclb200_batch* b, uint32_t* d_dst);
+int ipclb200_encrypt_batch(const ipclb200_pubkey* pk, const ipclb200_batch* pt,
+                           const ipclb200_batch* r, int r_bits, int make_secure,
+                           ipclb200_batch* ct);
+int ipclb200_decrypt_batch(const ipclb200_privkey* sk, const ipclb200_batch* ct,
+                           int use_crt, ipclb200_batch* pt);
+int ipclb200_modmul_batch(const ipclb200_batch* a, const ipclb200_batch* b,
+                          const uint32_t* h_b_shared, const uint32_t* h_mod,
+                          int mod_words, ipclb200_batch* out);
+int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
+                          const uint32_t* h_exp_shared, int exp_words, int exp_bits,
+                          const uint32_t* h_mod, int mod_words, ipclb200_batch* out);
 
 /* ---- measurement helpers --------------------------------------------------
  * Runs the integer-pipe microbenchmark (dependent-carry IMAD.WIDE.U32 chains on

@@ -53,7 +53,7 @@ def _nvcc():
 def _cuda_sources():
     srcs = [os.path.join(CSRC, f) for f in
             ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "mont_hensel.cuh",
-             "hostbn.hpp")]
+             "host_common.hpp", "hostbn.hpp")]
     exp = os.path.join(CSRC, "experiments")
     srcs += sorted(os.path.join(exp, f) for f in os.listdir(exp))
     srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))

@@ -36,6 +36,13 @@ EXPORTS = [
     "ipclb200_dev_free", "ipclb200_dev_upload", "ipclb200_dev_download",
     "ipclb200_dev_copy", "ipclb200_sync", "ipclb200_class_words",
     "ipclb200_debug_montsqr", "ipclb200_int_peak_sustained",
+    "ipclb200_init_devices", "ipclb200_active_devices", "ipclb200_has_experiments",
+    "ipclb200_pubkey_set_table_policy", "ipclb200_batch_alloc", "ipclb200_batch_free",
+    "ipclb200_batch_count", "ipclb200_batch_words", "ipclb200_batch_num_shards",
+    "ipclb200_batch_shard", "ipclb200_batch_upload", "ipclb200_batch_download",
+    "ipclb200_batch_sync", "ipclb200_batch_scatter", "ipclb200_batch_gather",
+    "ipclb200_encrypt_batch", "ipclb200_decrypt_batch", "ipclb200_modmul_batch",
+    "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
 ]
 
 
@@ -53,6 +60,8 @@ def lib():
         L.ipclb200_last_error.restype = ctypes.c_char_p
         L.ipclb200_version.restype = ctypes.c_char_p
         L.ipclb200_launch_count.restype = ctypes.c_uint64
+        L.ipclb200_batch_count.restype = ctypes.c_size_t
+        L.ipclb200_stream.restype = ctypes.c_void_p
         _lib = L
     return _lib
 
@@ -76,6 +85,20 @@ def _vp(x):
 
 def init(device=-1):
     _check(lib().ipclb200_init(int(device)))
+
+
+def init_devices(n=0):
+    """one process, n GPUs (0 = all visible): batches are split over them"""
+    _check(lib().ipclb200_init_devices(int(n)))
+    return lib().ipclb200_active_devices()
+
+
+def active_devices():
+    return lib().ipclb200_active_devices()
+
+
+def has_experiments():
+    return bool(lib().ipclb200_has_experiments())
 
 
 def shutdown():
@@ -160,6 +183,14 @@ class PubKey:
                                       int(make_secure), _p(ct)))
         return ct
 
+    def set_table_policy(self, max_table_mb=-1, upgrade_after=-1):
+        _check(lib().ipclb200_pubkey_set_table_policy(
+            self._h, ctypes.c_long(max_table_mb), ctypes.c_long(upgrade_after)))
+
+    def encrypt_batch(self, pt, r, ct, r_bits=0, make_secure=True):
+        _check(lib().ipclb200_encrypt_batch(self._h, pt._h, None if r is None else r._h,
+                                            int(r_bits), int(make_secure), ct._h))
+
     def encrypt_dev(self, d_pt, pt_words, d_r, r_words, count, d_ct, stream,
                     make_secure=True):
         _check(lib().ipclb200_encrypt_dev(self._h, _vp(d_pt), pt_words, _vp(d_r),
@@ -211,6 +242,9 @@ class PrivKey:
                                            ctypes.byref(xw)))
         return x
 
+    def decrypt_batch(self, ct, pt, use_crt=True):
+        _check(lib().ipclb200_decrypt_batch(self._h, ct._h, int(use_crt), pt._h))
+
     def decrypt_dev(self, d_ct, count, d_pt, stream, use_crt=True):
         _check(lib().ipclb200_decrypt_dev(self._h, _vp(d_ct), ctypes.c_size_t(count),
                                           int(use_crt), _vp(d_pt), _vp(stream)))
@@ -241,3 +275,80 @@ def modmul_dev(d_a, d_b, mod, count, d_out, stream, flags=0):
     _check(lib().ipclb200_modmul_dev(_vp(d_a), _vp(d_b), _p(mod), mod.shape[-1],
                                      ctypes.c_size_t(count), flags, _vp(d_out),
                                      _vp(stream)))
+
+
+class Batch:
+    """count x words limbs in HBM, sharded over the active devices
+    (ipclb200_batch_*)."""
+
+    def __init__(self, count, words):
+        self.count, self.words = int(count), int(words)
+        self._h = ctypes.c_void_p()
+        _check(lib().ipclb200_batch_alloc(ctypes.c_size_t(self.count), self.words,
+                                          ctypes.byref(self._h)))
+
+    @classmethod
+    def from_host(cls, a, words=None):
+        a = np.atleast_2d(_c(a))
+        b = cls(a.shape[0], words or a.shape[1])
+        b.upload(a)
+        return b
+
+    def upload(self, a):
+        a = np.atleast_2d(_c(a))
+        assert a.shape[0] == self.count
+        _check(lib().ipclb200_batch_upload(self._h, _p(a), a.shape[1]))
+
+    def download(self, words=None, out=None):
+        w = words or self.words
+        o = out if out is not None else np.zeros((self.count, w), dtype=np.uint32)
+        _check(lib().ipclb200_batch_download(self._h, _p(o), w))
+        return o
+
+    def sync(self):
+        _check(lib().ipclb200_batch_sync(self._h))
+
+    def scatter_from(self, d_src):
+        _check(lib().ipclb200_batch_scatter(self._h, _vp(d_src)))
+
+    def gather_to(self, d_dst):
+        _check(lib().ipclb200_batch_gather(self._h, _vp(d_dst)))
+
+    def shards(self):
+        out = []
+        for i in range(lib().ipclb200_batch_num_shards(self._h)):
+            dev, ptr = ctypes.c_int(), ctypes.c_void_p()
+            begin, count = ctypes.c_size_t(), ctypes.c_size_t()
+            stream = ctypes.c_void_p()
+            _check(lib().ipclb200_batch_shard(self._h, i, ctypes.byref(dev), ctypes.byref(ptr),
+                                              ctypes.byref(begin), ctypes.byref(count),
+                                              ctypes.byref(stream)))
+            out.append(dict(device=dev.value, ptr=ptr.value, begin=begin.value,
+                            count=count.value, stream=stream.value))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().ipclb200_batch_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def modmul_batch(a, b, mod, out, b_shared=None):
+    mod = _c(mod)
+    sh = None if b_shared is None else _c(b_shared)
+    _check(lib().ipclb200_modmul_batch(a._h, None if b is None else b._h, _p(sh), _p(mod),
+                                       mod.shape[-1], out._h))
+
+
+def modexp_batch(base, exp, mod, out, exp_shared=None, exp_bits=0):
+    mod = _c(mod)
+    sh = None if exp_shared is None else _c(exp_shared)
+    ew = exp.words if exp is not None else sh.shape[-1]
+    _check(lib().ipclb200_modexp_batch(base._h, None if exp is None else exp._h, _p(sh), ew,
+                                       int(exp_bits), _p(mod), mod.shape[-1], out._h))

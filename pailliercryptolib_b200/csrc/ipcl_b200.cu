@@ -2,10 +2,27 @@
 //
 // Host side of the boundary: argument checking, derivation of the per-modulus
 // Montgomery constants (hostbn.hpp), staging of the flat limb buffers, launch
-// configuration, and the error convention.  All arithmetic on batch elements
-// happens in the kernels of kernels.cuh; nothing here falls back to the CPU.
+// configuration, sharding of a batch over the GPUs of the box, and the error
+// convention.  All arithmetic on batch elements happens in the kernels of
+// kernels.cuh; nothing here falls back to the CPU.
+//
+// Runtime model
+//   * one Dev per CUDA device in use (created lazily), with a pool of streams;
+//     every host-pointer call takes its own stream from the pool and allocates
+//     its temporaries stream-ordered (cudaMallocAsync), so concurrent callers
+//     -- the reference calls encrypt/decrypt from 4 OpenMP threads on one key,
+//     test/test_cryptography.cpp:45-57 -- overlap instead of queueing on a lock;
+//   * keys keep their host-side constants and replicate the device blocks per
+//     device on first use;
+//   * host-pointer entry points split a batch into contiguous blocks over the
+//     active devices (ipclb200_init_devices): the slot of the reference's
+//     prefix/suffix split between CPU and accelerator, ipcl/mod_exp.cpp:702-731;
+//   * ipclb200_batch_* hold a batch sharded over the active devices in HBM;
+//     scatter/gather from/to one device go through NCCL send/recv.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -17,421 +34,307 @@
 #include <vector>
 
 #include "../../include/ipcl_b200.h"
+#include "host_common.hpp"
 #include "hostbn.hpp"
 #include "kernels.cuh"
-#ifdef IPCLB200_EXPERIMENTS
-#include "experiments/kernels_exp.cuh"
-#endif
 
 using namespace ipclb200;
+using namespace ipclb200::host;
 using hbn::Limbs;
 
 namespace {
 
-thread_local std::string t_err;
-
-int fail(int code, const std::string& msg) {
-  t_err = msg;
-  return code;
-}
-
-#define CUDA_TRY(expr)                                                   \
-  do {                                                                   \
-    cudaError_t e_ = (expr);                                             \
-    if (e_ != cudaSuccess)                                               \
-      return fail(IPCLB200_ERR_CUDA,                                     \
-                  std::string(#expr) + ": " + cudaGetErrorString(e_));   \
-  } while (0)
-
-#define TRY(expr)            \
-  do {                       \
-    int rc_ = (expr);        \
-    if (rc_ != 0) return rc_; \
-  } while (0)
+constexpr int kMaxDevices = 64;
 
 // ---------------------------------------------------------------------------
-// size classes: modulus words -> (limbs per lane K, lanes per integer T)
-// ---------------------------------------------------------------------------
-const int kClasses[] = {16, 32, 48, 64, 96, 128, 192, 256};
-// largest number of jobs for which the wide (4 limbs per lane) layout is used
-// (measured crossovers, profiles/r01_wide_layout.md)
-constexpr size_t kWideMax32 = 6144, kWideMax64 = 3072, kWideMax128 = 1536;
-// ... and for the middle layout (8 limbs per lane)
-constexpr size_t kMidMax32 = 12288, kMidMax64 = 6144, kMidMax128 = 3072;
-
-int class_words(int words) {
-  for (int c : kClasses)
-    if (words <= c) return c;
-  return 0;
-}
-
-#define IPCLB200_DISPATCH(L, F)            \
-  switch (L) {                             \
-    case 16:  F(8, 2); break;              \
-    case 32:  F(16, 2); break;             \
-    case 48:  F(12, 4); break;             \
-    case 64:  F(16, 4); break;             \
-    case 96:  F(12, 8); break;             \
-    case 128: F(16, 8); break;             \
-    case 192: F(12, 16); break;            \
-    case 256: F(16, 16); break;            \
-    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
-  }
-
-// Small batches: the same kernels with one integer spread over four times as
-// many lanes (4 limbs per lane).  A batch that cannot fill the 148 SMs is
-// latency bound -- a modexp is ~1200-2500 dependent Montgomery products -- and
-// the wide layout shortens every product (8 multiplies per row and lane
-// instead of 32) at the price of more shuffles per multiply.
-#define IPCLB200_DISPATCH_WIDE(L, F)       \
-  switch (L) {                             \
-    case 32:  F(4, 8); break;              \
-    case 64:  F(4, 16); break;             \
-    case 128: F(4, 32); break;             \
-    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
-  }
-
-// in between: 8 limbs per lane, twice the default number of lanes
-#define IPCLB200_DISPATCH_MID(L, F)        \
-  switch (L) {                             \
-    case 32:  F(8, 4); break;              \
-    case 64:  F(8, 8); break;              \
-    case 128: F(8, 16); break;             \
-    default: return fail(IPCLB200_ERR_UNSUPPORTED, "unsupported width"); \
-  }
-
-// 0 = default layout, 1 = wide (4 limbs per lane), 2 = middle (8 limbs per
-// lane); tasks = independent big-integer jobs of L words in the launch
-int pick_layout(size_t tasks, int L);
-bool use_wide(size_t tasks, int L) { return pick_layout(tasks, L) == 1; }
-
-int pick_layout(size_t tasks, int L) {
-  if (!(L == 32 || L == 64 || L == 128)) return 0;
-  const char* e = getenv("IPCLB200_WIDE");
-  if (e && e[0] == '0') return 0;
-  if (e && e[0] == '1') return 1;
-  if (e && e[0] == '2') return 2;
-  {
-    size_t wide_max = 0, mid_max = 0;
-    switch (L) {
-      case 32: wide_max = kWideMax32; mid_max = kMidMax32; break;
-      case 64: wide_max = kWideMax64; mid_max = kMidMax64; break;
-      default: wide_max = kWideMax128; mid_max = kMidMax128; break;
-    }
-    if (const char* m = getenv("IPCLB200_WIDE_MAX")) wide_max = strtoul(m, nullptr, 10);
-    if (const char* m = getenv("IPCLB200_MID_MAX")) mid_max = strtoul(m, nullptr, 10);
-    if (tasks <= wide_max) return 1;
-    if (tasks <= mid_max) return 2;
-    return 0;
-  }
-}
-
-int lanes_for(int L) {
-  switch (L) {
-    case 16: case 32: return 2;
-    case 48: case 64: return 4;
-    case 96: case 128: return 8;
-    default: return 16;
-  }
-}
-
-// fixed-window width minimising (2^w - 2) + bits + bits/w multiplies
-int pick_window(int ebits) {
-  int best = 1;
-  long best_cost = -1;
-  for (int w = 1; w <= kMaxWindow; w++) {
-    long cost = ((1L << w) - 2) + ebits + (ebits + w - 1) / w;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = w;
-    }
-  }
-  return best;
-}
-
-constexpr int kSchedWindow = 5;  // 16 odd powers per table
-
-#ifdef IPCLB200_EXPERIMENTS
-// byte code for decrypt_tile_kernel (opcodes: kernels.cuh) from a
-// sliding-window schedule: reduce the ciphertext, enter Montgomery form, build
-// the odd powers x, x^3, ... with x^2 parked in an extra slot, run the
-// schedule, leave Montgomery form
-std::vector<uint8_t> build_tile_program(const std::vector<uint8_t>& sched) {
-  const int nodd = sched[0];
-  std::vector<uint8_t> p = {0xc0, 0xc1, 0x40};
-  if (nodd > 1) {
-    p.push_back(0x00);
-    p.push_back((uint8_t)(0x40 + nodd));
-    p.push_back(0x80);
-    for (int k = 1; k < nodd; k++) {
-      p.push_back((uint8_t)(0x01 + nodd));
-      p.push_back((uint8_t)(0x40 + k));
-    }
-  }
-  p.push_back((uint8_t)(0x80 + sched[1]));
-  for (size_t i = 2; sched[i] != 0xff; i++)
-    p.push_back(sched[i] == 0 ? 0x00 : sched[i]);  // multiply by slot op-1
-  p.push_back(0xc2);
-  return p;
-}
-
-#endif
-
-// left-to-right sliding-window schedule for a fixed exponent (format: see
-// modexp_sched_core in kernels.cuh).  e > 0.
-std::vector<uint8_t> build_schedule(const Limbs& e, int w) {
-  std::vector<uint8_t> s;
-  s.push_back((uint8_t)(1 << (w - 1)));
-  auto bit = [&](int i) { return i >= 0 && ((e[(size_t)i / 32] >> (i % 32)) & 1u); };
-  int i = hbn::bitlen(e) - 1;
-  bool first = true;
-  while (i >= 0) {
-    if (!bit(i)) {
-      s.push_back(0);
-      i--;
-      continue;
-    }
-    int l = i - w + 1;
-    if (l < 0) l = 0;
-    while (!bit(l)) l++;
-    unsigned v = 0;
-    for (int k = i; k >= l; k--) v = (v << 1) | (bit(k) ? 1u : 0u);
-    if (first) {
-      s.push_back((uint8_t)((v - 1) / 2));
-      first = false;
-    } else {
-      for (int k = i; k >= l; k--) s.push_back(0);
-      s.push_back((uint8_t)((v - 1) / 2 + 1));
-    }
-    i = l - 1;
-  }
-  s.push_back(0xff);
-  return s;
-}
-
-// decrypt_hensel_kernel's schedule: the byte schedule of build_schedule as 32-bit
-// words [nodd, first, (run << 8 | entry)..., (run << 8 | 0xff)]: `run` squarings,
-// then a multiply by odd power `entry` (0xff: none, end)
-std::vector<uint32_t> hensel_schedule(const std::vector<uint8_t>& sched) {
-  std::vector<uint32_t> out = {sched[0], sched[1]};
-  uint32_t run = 0;
-  for (size_t i = 2; sched[i] != 0xff; i++) {
-    if (sched[i] == 0) {
-      run++;
-    } else {
-      out.push_back((run << 8) | (uint32_t)(sched[i] - 1));
-      run = 0;
-    }
-  }
-  out.push_back((run << 8) | 0xffu);
-  return out;
-}
-
-// per-side constants of the two-digit decrypt (10*pl words):
-//   p | pairs (k0_j, kw_j) of R^(j+1) mod p^2 in Montgomery form, j = 0..3 | -hp mod p
-// A pair (x0, w) stands for x0 - w*p mod p^2 (mont_hensel.cuh).
-void hensel_side_block(const Limbs& p, const Limbs& psq, const Limbs& hp, int pl,
-                       uint32_t* out) {
-  hbn::to_words(p, out, pl);
-  const Limbs R = hbn::pow2(32u * (unsigned)pl);
-  Limbs t = hbn::mod(R, psq);  // R^1
-  for (int j = 0; j < 4; j++) {
-    t = hbn::mod(hbn::mul(t, R), psq);  // R^(j+2) = R^(j+1) in Montgomery form
-    Limbs hi, lo;
-    hbn::divmod(t, p, &hi, &lo);
-    Limbs wneg = hbn::mod(hi, p);
-    Limbs w = hbn::is_zero(wneg) ? wneg : hbn::sub(p, wneg);
-    hbn::to_words(lo, out + (size_t)(1 + 2 * j) * pl, pl);
-    hbn::to_words(w, out + (size_t)(2 + 2 * j) * pl, pl);
-  }
-  Limbs nhp = hbn::is_zero(hp) ? hp : hbn::sub(p, hp);
-  hbn::to_words(nhp, out + (size_t)9 * pl, pl);
-}
-
-#ifdef IPCLB200_EXPERIMENTS
-// FP64 role (mont_fp64.cuh): the 64-word class (p^2 of a 2048-bit key) as 96
-// limbs of 22 bits over 4 lanes
-constexpr int kFpWords = 64;
-constexpr int kFpK = 24, kFpT = 4;
-constexpr int kFpLimbs = kFpK * kFpT;
-
-void fp_limbs(const Limbs& x, double* out, int L) {
-  for (int g = 0; g < L; g++) {
-    const unsigned off = (unsigned)kFpW * (unsigned)g;
-    const size_t idx = off / 32;
-    const unsigned sh = off % 32;
-    uint64_t v = 0;
-    if (idx < x.size()) v = x[idx];
-    if (idx + 1 < x.size()) v |= (uint64_t)x[idx + 1] << 32;
-    out[g] = (double)((v >> sh) & kFpMask);
-  }
-}
-
-#endif
-
-// ---------------------------------------------------------------------------
-// per-modulus constants
+// per-modulus constants on one device
 // ---------------------------------------------------------------------------
 struct DevModulus {
   int L = 0;
+  int device = -1;
   Limbs n;
   uint32_t* d = nullptr;  // [n | rr | r3 | one] each L words, then n0inv
   const uint32_t* d_n0inv = nullptr;
   ModConst mc{};
   ~DevModulus() {
-    if (d) cudaFree(d);
+    if (d) {
+      cudaSetDevice(device);
+      cudaFree(d);
+    }
   }
 };
 
-struct HostModConst {
-  std::vector<uint32_t> n, rr, r3, one;
-  uint32_t n0inv;
-  uint32_t small_mod;
-};
-
-void host_mod_const(const Limbs& n, int L, HostModConst* h) {
-  Limbs R = hbn::pow2(32u * (unsigned)L);
-  Limbs one = hbn::mod(R, n);
-  Limbs rr = hbn::mod(hbn::mul(one, one), n);
-  Limbs r3 = hbn::mod(hbn::mul(rr, one), n);
-  h->n.resize(L);
-  h->rr.resize(L);
-  h->r3.resize(L);
-  h->one.resize(L);
-  hbn::to_words(n, h->n.data(), L);
-  hbn::to_words(rr, h->rr.data(), L);
-  hbn::to_words(r3, h->r3.data(), L);
-  hbn::to_words(one, h->one.data(), L);
-  h->n0inv = hbn::neg_inv32(n[0]);
-  h->small_mod = hbn::bitlen(n) <= 32 * L - 2 ? 1u : 0u;
-}
-
 // ---------------------------------------------------------------------------
-// context
+// devices
 // ---------------------------------------------------------------------------
-struct Ctx {
-  std::mutex mu;
-  bool ready = false;
-  int device = -1;
+struct Dev {
+  int id = -1;
   int sms = 0;
-  cudaStream_t stream = nullptr;
-  // second stream + events for the two-kernel dual-pipe decrypt
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // grow-only scratch buffers for the host-pointer entry points
-  static const int kSlots = 10;
-  uint32_t* scratch[kSlots] = {};
-  size_t scratch_words[kSlots] = {};
-  // window-table workspace per stream
-  std::map<void*, std::pair<uint32_t*, size_t>> table_ws;
-  // small cache of shared moduli
+  cudaStream_t stream = nullptr;  // the device's library stream (batches, dev_*)
+  cudaStream_t side = nullptr;    // fixed-base table builds
+  std::mutex mu;                  // stream pool, modulus cache, table accounting
+  std::vector<cudaStream_t> idle;
   std::vector<std::shared_ptr<DevModulus>> mod_cache;
-  std::atomic<uint64_t> launches{0};
+  size_t comb_bytes = 0;  // bytes of wide fixed-base tables alive on this device
 };
 
-Ctx g_ctx;
-int g_requested_device = -1;  // set by ipclb200_init(device >= 0)
+struct Runtime {
+  std::mutex mu;
+  std::atomic<Dev*> dev[kMaxDevices];
+  std::vector<int> active;  // device ordinals host-pointer batches are split over
+  bool active_set = false;
+  std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> use_clock{0};
+  Runtime() {
+    for (auto& d : dev) d.store(nullptr);
+  }
+};
+Runtime g;
 
-int ensure_init_locked() {
-  if (g_ctx.ready) {
-    CUDA_TRY(cudaSetDevice(g_ctx.device));
+int device_count_raw() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
     return 0;
   }
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail(IPCLB200_ERR_NO_DEVICE,
-                std::string("no CUDA device: ") + cudaGetErrorString(e));
-  int dev = 0;
-  if (g_requested_device >= 0) {
-    dev = g_requested_device;
-  } else if (const char* lr = getenv("LOCAL_RANK")) {
-    dev = atoi(lr) % ndev;  // one process per GPU under torchrun
-  } else {
-    cudaGetDevice(&dev);
+  return n;
+}
+
+// the Dev of CUDA device `id`, created on first use
+int dev_get(int id, Dev** out) {
+  if (id < 0 || id >= kMaxDevices) return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
+  Dev* d = g.dev[id].load(std::memory_order_acquire);
+  if (!d) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    d = g.dev[id].load(std::memory_order_acquire);
+    if (!d) {
+      if (id >= device_count_raw())
+        return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
+      cudaDeviceProp prop;
+      CUDA_TRY(cudaGetDeviceProperties(&prop, id));
+      if (prop.major != 10)
+        return fail(IPCLB200_ERR_NO_DEVICE,
+                    std::string("device is sm_") + std::to_string(prop.major) +
+                        std::to_string(prop.minor) +
+                        ", this library holds sm_100a code only");
+      CUDA_TRY(cudaSetDevice(id));
+      std::unique_ptr<Dev> nd(new Dev);
+      nd->id = id;
+      nd->sms = prop.multiProcessorCount;
+      CUDA_TRY(cudaStreamCreateWithFlags(&nd->stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&nd->side, cudaStreamNonBlocking));
+      {
+        // temporaries and batches come from the stream-ordered pool: keep freed
+        // blocks cached instead of returning them to the OS at every synchronise
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+          uint64_t keep = ~(uint64_t)0;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+      }
+      d = nd.release();
+      g.dev[id].store(d, std::memory_order_release);
+    }
   }
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10)
-    return fail(IPCLB200_ERR_NO_DEVICE,
-                std::string("device is sm_") + std::to_string(prop.major) +
-                    std::to_string(prop.minor) +
-                    ", this library holds sm_100a code only");
-  CUDA_TRY(cudaSetDevice(dev));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.aux_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
+  *out = d;
+  return 0;
+}
+
+// the devices a host-pointer batch is split over; the first one is the primary
+// device (key set-up scalars, ipclb200_stream(), dev_alloc ...)
+int active_devices(std::vector<Dev*>* out) {
+  std::vector<int> ids;
   {
-    // device-resident batches come from the stream-ordered pool: keep freed
-    // blocks cached instead of returning them to the OS at every synchronise
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = ~(uint64_t)0;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.active_set) {
+      const int ndev = device_count_raw();
+      if (ndev == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+      int dev = 0;
+      const char* many = getenv("IPCLB200_DEVICES");
+      if (many && *many) {
+        // one process, several GPUs without an explicit ipclb200_init_devices
+        int n = !strcmp(many, "all") ? ndev : atoi(many);
+        if (n <= 0 || n > ndev) n = ndev;
+        g.active.clear();
+        for (int i = 0; i < n; i++) g.active.push_back(i);
+      } else {
+        if (const char* lr = getenv("LOCAL_RANK")) {
+          dev = atoi(lr) % ndev;  // one process per GPU under torchrun
+        } else if (cudaGetDevice(&dev) != cudaSuccess) {
+          cudaGetLastError();
+          dev = 0;
+        }
+        g.active = {dev};
+      }
+      g.active_set = true;
     }
+    ids = g.active;
+  }
+  out->clear();
+  for (int id : ids) {
+    Dev* d = nullptr;
+    TRY(dev_get(id, &d));
+    out->push_back(d);
+  }
+  return 0;
+}
+
+int primary_device(Dev** out) {
+  std::vector<Dev*> devs;
+  TRY(active_devices(&devs));
+  *out = devs[0];
+  return 0;
+}
+
+// the Dev that owns a device pointer
+int dev_of_pointer(const void* p, Dev** out) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess ||
+      (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
     cudaGetLastError();
+    if (device_count_raw() == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+    return fail(IPCLB200_ERR_BAD_ARG, "not a device pointer");
   }
-  g_ctx.device = dev;
-  g_ctx.sms = prop.multiProcessorCount;
-  g_ctx.ready = true;
-  return 0;
+  return dev_get(at.device, out);
 }
 
-int scratch_get(int slot, size_t words, uint32_t** out) {
-  if (g_ctx.scratch_words[slot] < words) {
-    if (g_ctx.scratch[slot]) {
-      // the *_dev entry points enqueue on caller streams: wait for all of them
-      CUDA_TRY(cudaDeviceSynchronize());
-      CUDA_TRY(cudaFree(g_ctx.scratch[slot]));
-      g_ctx.scratch[slot] = nullptr;
-      g_ctx.scratch_words[slot] = 0;
-    }
-    size_t want = words + words / 4 + 1024;
-    CUDA_TRY(cudaMalloc(&g_ctx.scratch[slot], want * sizeof(uint32_t)));
-    g_ctx.scratch_words[slot] = want;
+// ---------------------------------------------------------------------------
+// one operation on one device: a stream plus stream-ordered temporaries
+// ---------------------------------------------------------------------------
+struct Op {
+  Dev* dev = nullptr;
+  cudaStream_t s = nullptr;
+  bool pooled = false;
+  std::vector<void*> tmp;
+
+  Op() = default;
+  Op(const Op&) = delete;
+  Op& operator=(const Op&) = delete;
+  Op(Op&& o) noexcept { *this = std::move(o); }
+  Op& operator=(Op&& o) noexcept {
+    dev = o.dev;
+    s = o.s;
+    pooled = o.pooled;
+    tmp = std::move(o.tmp);
+    o.dev = nullptr;
+    o.s = nullptr;
+    o.pooled = false;
+    return *this;
   }
-  *out = g_ctx.scratch[slot];
-  return 0;
-}
 
-int table_ws_get(void* stream, size_t words, uint32_t** out) {
-  auto& slot = g_ctx.table_ws[stream];
-  if (slot.second < words) {
-    if (slot.first) {
-      CUDA_TRY(cudaDeviceSynchronize());
-      CUDA_TRY(cudaFree(slot.first));
-      slot = {nullptr, 0};
+  // on a stream of the library's pool (host-pointer calls)
+  int open(Dev* d) {
+    dev = d;
+    CUDA_TRY(cudaSetDevice(d->id));
+    {
+      std::lock_guard<std::mutex> lk(d->mu);
+      if (!d->idle.empty()) {
+        s = d->idle.back();
+        d->idle.pop_back();
+      }
     }
-    uint32_t* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, words * sizeof(uint32_t)));
-    slot = {p, words};
+    if (!s) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    pooled = true;
+    return 0;
   }
-  *out = slot.first;
-  return 0;
-}
-
-// table workspace of `words` words plus the zeroed work counter behind it
-int table_ws_with_counter(cudaStream_t s, size_t words, uint32_t** ws,
-                          unsigned int** counter, int key = 0) {
-  words = (words + 3) & ~(size_t)3;
-  TRY(table_ws_get((void*)((uintptr_t)s + (uintptr_t)key), words + 4, ws));
-  *counter = reinterpret_cast<unsigned int*>(*ws + words);
-  CUDA_TRY(cudaMemsetAsync(*counter, 0, 16, s));
-  return 0;
-}
-
-int make_modulus(const Limbs& n, int L, std::shared_ptr<DevModulus>* out) {
-  for (auto& m : g_ctx.mod_cache)
-    if (m->L == L && m->n == n) {
-      *out = m;
-      return 0;
+  // on a caller's stream (*_dev calls, batches): only enqueues
+  int open_on(Dev* d, cudaStream_t user) {
+    dev = d;
+    CUDA_TRY(cudaSetDevice(d->id));
+    s = user;
+    pooled = false;
+    return 0;
+  }
+  int alloc(size_t bytes, void** out) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+    tmp.push_back(p);
+    *out = p;
+    return 0;
+  }
+  int words(size_t n, uint32_t** out) { return alloc(n * sizeof(uint32_t), (void**)out); }
+  int sync() {
+    CUDA_TRY(cudaSetDevice(dev->id));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+  }
+  // releases the temporaries (stream-ordered: after the work enqueued so far)
+  void close() {
+    if (!dev) return;
+    cudaSetDevice(dev->id);
+    for (void* p : tmp) cudaFreeAsync(p, s);
+    tmp.clear();
+    if (pooled && s) {
+      std::lock_guard<std::mutex> lk(dev->mu);
+      dev->idle.push_back(s);
     }
+    dev = nullptr;
+    s = nullptr;
+  }
+  ~Op() { close(); }
+};
+
+// restores the caller's current device when a multi-device call returns
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// contiguous block partition of a batch over the active devices.
+// A device gets a block only if at least `min_block` elements are left for it,
+// so that small batches stay on one GPU.
+struct Shard {
+  Dev* dev;
+  size_t begin, count;
+};
+constexpr size_t kMinShard = 512;
+
+int plan_shards(size_t count, std::vector<Shard>* out) {
+  std::vector<Dev*> devs;
+  TRY(active_devices(&devs));
+  size_t min_block = kMinShard;
+  if (const char* e = getenv("IPCLB200_MIN_SHARD")) min_block = strtoul(e, nullptr, 10);
+  if (min_block < 1) min_block = 1;
+  size_t use = std::min<size_t>(devs.size(), std::max<size_t>(1, count / min_block));
+  out->clear();
+  const size_t base = count / use, rem = count % use;
+  size_t at = 0;
+  for (size_t i = 0; i < use; i++) {
+    const size_t c = base + (i < rem ? 1 : 0);
+    out->push_back({devs[i], at, c});
+    at += c;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// modulus cache
+// ---------------------------------------------------------------------------
+int make_modulus(Dev* dev, const Limbs& n, int L, std::shared_ptr<DevModulus>* out) {
+  {
+    std::lock_guard<std::mutex> lk(dev->mu);
+    for (auto& m : dev->mod_cache)
+      if (m->L == L && m->n == n) {
+        *out = m;
+        return 0;
+      }
+  }
   auto m = std::make_shared<DevModulus>();
   HostModConst h;
   host_mod_const(n, L, &h);
   m->L = L;
   m->n = n;
+  m->device = dev->id;
+  CUDA_TRY(cudaSetDevice(dev->id));
   CUDA_TRY(cudaMalloc(&m->d, sizeof(uint32_t) * (4 * (size_t)L + 4)));
   std::vector<uint32_t> blk;
   blk.insert(blk.end(), h.n.begin(), h.n.end());
@@ -448,33 +351,23 @@ int make_modulus(const Limbs& n, int L, std::shared_ptr<DevModulus>* out) {
   m->d_n0inv = m->d + 4 * L;
   m->mc.n0inv = h.n0inv;
   m->mc.small_mod = h.small_mod;
-  if (g_ctx.mod_cache.size() >= 16) g_ctx.mod_cache.erase(g_ctx.mod_cache.begin());
-  g_ctx.mod_cache.push_back(m);
+  std::lock_guard<std::mutex> lk(dev->mu);
+  if (dev->mod_cache.size() >= 32) dev->mod_cache.erase(dev->mod_cache.begin());
+  dev->mod_cache.push_back(m);
   *out = m;
-  return 0;
-}
-
-int check_modulus(const uint32_t* mod, int words, Limbs* out) {
-  Limbs n = hbn::from_words(mod, words);
-  if (n.empty()) return fail(IPCLB200_ERR_BAD_ARG, "modulus is zero");
-  if (!(n[0] & 1u))
-    return fail(IPCLB200_ERR_EVEN_MODULUS,
-                "modulus is even (Montgomery arithmetic needs an odd modulus)");
-  *out = n;
   return 0;
 }
 
 // grid for a persistent kernel: enough blocks for `groups` groups, capped at
 // what is co-resident (a multiple of the SM count)
 template <typename Kern>
-int grid_for(Kern kern, size_t groups, int T, int* grid) {
+int grid_for(Dev* dev, Kern kern, size_t groups, int T, size_t smem, int* grid) {
   int per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
-                                                         kBlockThreads, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
   if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "kernel does not fit an SM");
   size_t gpb = kBlockThreads / T;
   size_t need = (groups + gpb - 1) / gpb;
-  size_t cap = (size_t)per_sm * g_ctx.sms;
+  size_t cap = (size_t)per_sm * dev->sms;
   if (need < 1) need = 1;
   // persistent grid: all resident blocks (work is claimed dynamically), or
   // just enough blocks when the batch is smaller than one wave
@@ -482,60 +375,54 @@ int grid_for(Kern kern, size_t groups, int T, int* grid) {
   return 0;
 }
 
-int max_bits(const uint32_t* v, int words, size_t count, size_t stride) {
-  int best = 0;
-  for (size_t i = 0; i < count; i++) {
-    const uint32_t* e = v + i * stride;
-    for (int w = words - 1; w >= 0; w--) {
-      if (e[w]) {
-        int b = w * 32 + 32 - __builtin_clz(e[w]);
-        if (b > best) best = b;
-        break;
-      }
-      if ((w + 1) * 32 <= best) break;
-    }
-  }
-  return best;
+// window-table workspace of `words` words plus the zeroed work counter behind it
+int table_ws(Op& op, size_t words, uint32_t** ws, unsigned int** counter) {
+  words = (words + 3) & ~(size_t)3;
+  TRY(op.words(words + 4, ws));
+  *counter = reinterpret_cast<unsigned int*>(*ws + words);
+  CUDA_TRY(cudaMemsetAsync(*counter, 0, 16, op.s));
+  return 0;
 }
 
 // host (count x words) -> device (count x L), zero padded
-int upload_padded(uint32_t* d, const uint32_t* h, int words, int L,
-                  size_t count, cudaStream_t s) {
+int upload_padded(uint32_t* d, const uint32_t* h, int words, int L, size_t count,
+                  cudaStream_t s) {
+  if (count == 0) return 0;
   if (words == L) {
     CUDA_TRY(cudaMemcpyAsync(d, h, count * (size_t)L * 4, cudaMemcpyHostToDevice, s));
   } else {
     CUDA_TRY(cudaMemsetAsync(d, 0, count * (size_t)L * 4, s));
-    CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)L * 4, h, (size_t)words * 4,
-                               (size_t)words * 4, count, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)L * 4, h, (size_t)words * 4, (size_t)words * 4,
+                               count, cudaMemcpyHostToDevice, s));
   }
   return 0;
 }
-int download_padded(uint32_t* h, const uint32_t* d, int words, int L,
-                    size_t count, cudaStream_t s) {
+int download_padded(uint32_t* h, const uint32_t* d, int words, int L, size_t count,
+                    cudaStream_t s) {
+  if (count == 0) return 0;
   if (words == L) {
     CUDA_TRY(cudaMemcpyAsync(h, d, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
   } else {
-    CUDA_TRY(cudaMemcpy2DAsync(h, (size_t)words * 4, d, (size_t)L * 4,
-                               (size_t)words * 4, count, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpy2DAsync(h, (size_t)words * 4, d, (size_t)L * 4, (size_t)words * 4,
+                               count, cudaMemcpyDeviceToHost, s));
   }
   return 0;
 }
 
 // ---------------------------------------------------------------------------
-// launch helpers (device pointers, any stream)
+// launch helpers (device pointers, the Op's stream)
 // ---------------------------------------------------------------------------
-int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
+int launch_modexp(Op& op, ModexpParams p, int L) {
   // a schedule needs 2^(kSchedWindow-1) table entries per group
   p.window = p.sched ? kSchedWindow - 1 : pick_window(p.exp_bits);
-  const int T = lanes_for(L);
   int grid = 0;
-#define F(K_, T_)                                                         \
-  {                                                                       \
-    TRY(grid_for(modexp_kernel<K_, T_>, p.count, T_, &grid));             \
-    size_t groups = (size_t)grid * (kBlockThreads / T_);                  \
-    TRY(table_ws_with_counter(s, groups * ((size_t)L << p.window),        \
-                              &p.table_ws, &p.work_counter));             \
-    modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
+#define F(K_, T_)                                                              \
+  {                                                                            \
+    TRY(grid_for(op.dev, modexp_kernel<K_, T_>, p.count, T_, 0, &grid));       \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                       \
+    TRY(table_ws(op, groups * ((size_t)L << p.window), &p.table_ws,            \
+                 &p.work_counter));                                            \
+    modexp_kernel<K_, T_><<<grid, kBlockThreads, 0, op.s>>>(p);                \
   }
   switch (pick_layout(p.count, L)) {
     case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
@@ -543,25 +430,72 @@ int launch_modexp(ModexpParams p, int L, cudaStream_t s) {
     default: IPCLB200_DISPATCH(L, F)
   }
 #undef F
-  (void)T;
-  g_ctx.launches++;
+  g.launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int launch_modmul(ModmulParams p, int L, cudaStream_t s) {
+int launch_modmul(Op& op, ModmulParams p, int L) {
   int grid = 0;
-#define F(K_, T_)                                               \
-  {                                                             \
-    TRY(grid_for(modmul_kernel<K_, T_>, p.count, T_, &grid));   \
-    modmul_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);    \
+  {
+    uint32_t* ws = nullptr;
+    TRY(table_ws(op, 0, &ws, &p.work_counter));
+  }
+#define F(K_, T_)                                                         \
+  {                                                                       \
+    TRY(grid_for(op.dev, modmul_kernel<K_, T_>, p.count, T_, 0, &grid));  \
+    modmul_kernel<K_, T_><<<grid, kBlockThreads, 0, op.s>>>(p);           \
   }
   IPCLB200_DISPATCH(L, F)
 #undef F
-  g_ctx.launches++;
+  g.launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+struct CombTable {
+  uint32_t* d = nullptr;
+  int w = 0, windows = 0;
+  bool full = false;  // built at the budget width
+  size_t bytes = 0;
+  cudaEvent_t ready = nullptr;  // recorded behind the build kernels
+};
+
+// device-side state of a public key on one device
+struct PubDev {
+  Dev* dev = nullptr;
+  std::shared_ptr<DevModulus> msq;
+  uint32_t* d_const = nullptr;  // [nR (L) | hs_m (L) | n as exponent (nl)]
+  uint8_t* d_sched_n = nullptr;
+  CombTable cur, next;
+  bool next_pending = false;
+  std::vector<CombTable> retired;  // replaced tables, freed with the key
+};
+
+void free_comb(Dev* dev, CombTable& t) {
+  if (t.d) {
+    cudaFree(t.d);
+    if (t.full) {
+      std::lock_guard<std::mutex> lk(dev->mu);
+      dev->comb_bytes -= std::min(dev->comb_bytes, t.bytes);
+    }
+  }
+  if (t.ready) cudaEventDestroy(t.ready);
+  t = CombTable{};
+}
+
+struct PrivDev {
+  Dev* dev = nullptr;
+  std::shared_ptr<DevModulus> mp2, mq2, mnsq;
+  uint32_t* d_const = nullptr;
+  uint8_t* d_sched = nullptr;
+  uint32_t* d_hensel = nullptr;
+#ifdef IPCLB200_EXPERIMENTS
+  double* d_fp = nullptr;
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
+};
 
 }  // namespace
 
@@ -574,93 +508,177 @@ struct ipclb200_pubkey {
   Limbs n, nsq, hs;
   bool djn = false;
   int rand_bits = 0;
-  std::shared_ptr<DevModulus> msq;
-  uint32_t* d_const = nullptr;  // [nR (L) | hs_m (L) | n as exponent (nl)]
-  // lazily built fixed-base comb table for hs
-  mutable uint32_t* d_comb = nullptr;
-  mutable int comb_w = 0;
-  mutable int comb_windows = 0;
-  mutable size_t enc_total = 0;  // elements encrypted with this key so far
-  mutable bool comb_full = false;  // the table was built at the budget width
-  uint8_t* d_sched_n = nullptr;  // sliding-window schedule of the exponent n
+  std::vector<uint32_t> h_const;
+  std::vector<uint8_t> h_sched_n;
+  // fixed-base table policy (ipclb200_pubkey_set_table_policy)
+  size_t comb_max_mb = 4096;
+  size_t comb_upgrade_at = 8192;
+  std::mutex mu;  // device replicas, table state, counters
+  size_t enc_total = 0;
+  std::unique_ptr<PubDev> dev[kMaxDevices];
   ~ipclb200_pubkey() {
-    if (d_const) cudaFree(d_const);
-    if (d_comb) cudaFree(d_comb);
-    if (d_sched_n) cudaFree(d_sched_n);
+    for (auto& pd : dev) {
+      if (!pd) continue;
+      if (g.dev[pd->dev->id].load() != pd->dev) continue;  // after shutdown
+      cudaSetDevice(pd->dev->id);
+      cudaDeviceSynchronize();
+      if (pd->d_const) cudaFree(pd->d_const);
+      if (pd->d_sched_n) cudaFree(pd->d_sched_n);
+      free_comb(pd->dev, pd->cur);
+      free_comb(pd->dev, pd->next);
+      for (auto& t : pd->retired) free_comb(pd->dev, t);
+    }
   }
 };
 
 struct ipclb200_privkey {
-  int pl = 0;  // words of p (and q)
-  int L = 0;   // class words of p^2 (== 2*pl required)
-  Limbs p, q, n, nsq, lambda;
-  std::shared_ptr<DevModulus> mp2, mq2, mnsq;
-  uint32_t* d_const = nullptr;
-  // offsets into d_const (words)
-  const uint32_t *d_p = nullptr, *d_q = nullptr, *d_pm1 = nullptr,
-                 *d_qm1 = nullptr, *d_hpR = nullptr, *d_hqR = nullptr,
-                 *d_pinvR = nullptr, *d_n = nullptr, *d_muR = nullptr,
-                 *d_lambda = nullptr;
-  uint32_t p_inv32 = 0, q_inv32 = 0, p_n0inv = 0, q_n0inv = 0, n_inv32 = 0,
-           n_n0inv = 0;
-  int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
-  // sliding-window schedules of the shared exponents p-1, q-1
-  uint8_t* d_sched = nullptr;
-  const uint8_t *d_sched_p = nullptr, *d_sched_q = nullptr,
-                *d_sched_lambda = nullptr;
-  // two-digit (Hensel) decrypt, mont_hensel.cuh: per side p | K_0..K_3 | -hp
-  // (10*pl words) and the run-length schedules; hensel_ok: p and q fill their
-  // pl words and pl is a layout of decrypt_hensel_kernel
-  uint32_t* d_hensel = nullptr;
-  const uint32_t *d_hblk_p = nullptr, *d_hblk_q = nullptr, *d_hsched_p = nullptr,
-                 *d_hsched_q = nullptr;
+  int pl = 0;    // words of p (and q)
+  int L = 0;     // class words of p^2
+  int Lnsq = 0;  // class words of n^2
+  Limbs p, q, n, nsq, psq, qsq, lambda;
+  // host images of the device blocks (replicated per device on first use)
+  std::vector<uint32_t> h_const;  // p q pm1 qm1 hpR hqR pinvR | n muR | n0inv | lambda
+  std::vector<uint8_t> h_sched;   // schedules of p-1, q-1, [experiments], lambda
+  size_t off_sched_q = 0, off_prog_p = 0, off_prog_q = 0, off_sched_lambda = 0;
+  std::vector<uint32_t> h_hensel;  // 10*pl per side, then the two run schedules
+  size_t off_hsched_p = 0, off_hsched_q = 0;
   bool hensel_ok = false;
+  uint32_t p_inv32 = 0, q_inv32 = 0, p_n0inv = 0, q_n0inv = 0, n_inv32 = 0, n_n0inv = 0;
+  int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
 #ifdef IPCLB200_EXPERIMENTS
-  // byte-code programs of the thread-per-integer kernel and -N^-1 mod 2^256
-  const uint8_t *d_prog_p = nullptr, *d_prog_q = nullptr;
   uint32_t ninv_p[8] = {}, ninv_q[8] = {};
   int tile_slots = 0;
-  // FP64-pipe constants (mont_fp64.cuh), only for the 64-word class of p^2
-  double* d_fp = nullptr;
-  FpModConst fp0{}, fp1{};
+  std::vector<double> h_fp;
+  uint32_t fp_n0inv_p = 0, fp_n0inv_q = 0;
   bool fp_ok = false;
 #endif
+  std::mutex mu;
+  std::unique_ptr<PrivDev> dev[kMaxDevices];
   ~ipclb200_privkey() {
-    if (d_const) cudaFree(d_const);
-    if (d_sched) cudaFree(d_sched);
-    if (d_hensel) cudaFree(d_hensel);
+    for (auto& sd : dev) {
+      if (!sd) continue;
+      if (g.dev[sd->dev->id].load() != sd->dev) continue;  // after shutdown
+      cudaSetDevice(sd->dev->id);
+      cudaDeviceSynchronize();
+      if (sd->d_const) cudaFree(sd->d_const);
+      if (sd->d_sched) cudaFree(sd->d_sched);
+      if (sd->d_hensel) cudaFree(sd->d_hensel);
 #ifdef IPCLB200_EXPERIMENTS
-    if (d_fp) cudaFree(d_fp);
+      if (sd->d_fp) cudaFree(sd->d_fp);
+      if (sd->aux_stream) cudaStreamDestroy(sd->aux_stream);
+      if (sd->ev_fork) cudaEventDestroy(sd->ev_fork);
+      if (sd->ev_join) cudaEventDestroy(sd->ev_join);
 #endif
+    }
   }
 };
 
 namespace {
 
-// single modexp on the device through the batch kernel (key-setup scalars:
-// what the reference routes to ippSBModExp, ipcl/mod_exp.cpp:535-585)
-int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
-                  Limbs* out);
+int pub_dev(const ipclb200_pubkey* pk_c, Dev* dev, PubDev** out) {
+  ipclb200_pubkey* pk = const_cast<ipclb200_pubkey*>(pk_c);
+  std::lock_guard<std::mutex> lk(pk->mu);
+  auto& slot = pk->dev[dev->id];
+  if (!slot) {
+    std::unique_ptr<PubDev> pd(new PubDev);
+    pd->dev = dev;
+    TRY(make_modulus(dev, pk->nsq, pk->L, &pd->msq));
+    CUDA_TRY(cudaSetDevice(dev->id));
+    CUDA_TRY(cudaMalloc(&pd->d_const, pk->h_const.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(pd->d_const, pk->h_const.data(),
+                        pk->h_const.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!pk->h_sched_n.empty()) {
+      CUDA_TRY(cudaMalloc(&pd->d_sched_n, pk->h_sched_n.size()));
+      CUDA_TRY(cudaMemcpy(pd->d_sched_n, pk->h_sched_n.data(), pk->h_sched_n.size(),
+                          cudaMemcpyHostToDevice));
+    }
+    slot = std::move(pd);
+  }
+  *out = slot.get();
+  return 0;
+}
 
-int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
-                     const uint32_t* mod, int mod_words, int exp_words,
-                     size_t count, unsigned flags, uint32_t* out) {
+int priv_dev(const ipclb200_privkey* sk_c, Dev* dev, PrivDev** out) {
+  ipclb200_privkey* sk = const_cast<ipclb200_privkey*>(sk_c);
+  std::lock_guard<std::mutex> lk(sk->mu);
+  auto& slot = sk->dev[dev->id];
+  if (!slot) {
+    std::unique_ptr<PrivDev> sd(new PrivDev);
+    sd->dev = dev;
+    TRY(make_modulus(dev, sk->psq, sk->L, &sd->mp2));
+    TRY(make_modulus(dev, sk->qsq, sk->L, &sd->mq2));
+    TRY(make_modulus(dev, sk->nsq, sk->Lnsq, &sd->mnsq));
+    CUDA_TRY(cudaSetDevice(dev->id));
+    CUDA_TRY(cudaMalloc(&sd->d_const, sk->h_const.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(sd->d_const, sk->h_const.data(),
+                        sk->h_const.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&sd->d_sched, sk->h_sched.size()));
+    CUDA_TRY(cudaMemcpy(sd->d_sched, sk->h_sched.data(), sk->h_sched.size(),
+                        cudaMemcpyHostToDevice));
+    if (sk->hensel_ok) {
+      CUDA_TRY(cudaMalloc(&sd->d_hensel, sk->h_hensel.size() * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemcpy(sd->d_hensel, sk->h_hensel.data(),
+                          sk->h_hensel.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+#ifdef IPCLB200_EXPERIMENTS
+    if (sk->fp_ok) {
+      CUDA_TRY(cudaMalloc(&sd->d_fp, sk->h_fp.size() * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(sd->d_fp, sk->h_fp.data(), sk->h_fp.size() * sizeof(double),
+                          cudaMemcpyHostToDevice));
+    }
+#endif
+    slot = std::move(sd);
+  }
+  *out = slot.get();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// generic modexp on one device
+// ---------------------------------------------------------------------------
+// shared modulus: device pointers in, device pointer out
+int modexp_shared_dev(Op& op, const uint32_t* d_base, const uint32_t* d_exp,
+                      const Limbs& n, int L, int exp_words, int exp_bits, size_t count,
+                      unsigned flags, const uint8_t* d_sched, uint32_t* d_out) {
+  std::shared_ptr<DevModulus> dm;
+  TRY(make_modulus(op.dev, n, L, &dm));
+  CUDA_TRY(cudaSetDevice(op.dev->id));
+  ModexpParams p{};
+  p.base = d_base;
+  p.base_stride = (flags & IPCLB200_SHARED_BASE) ? 0 : L;
+  p.exp = d_exp;
+  p.exp_stride = (flags & IPCLB200_SHARED_EXP) ? 0 : exp_words;
+  p.exp_words = exp_words;
+  p.exp_bits = exp_bits > 0 ? exp_bits : exp_words * 32;
+  p.n = dm->mc.n;
+  p.rr = dm->mc.rr;
+  p.one = dm->mc.one;
+  p.n0inv = dm->d_n0inv;
+  p.out = d_out;
+  p.count = count;
+  p.sched = d_sched;
+  return launch_modexp(op, p, L);
+}
+
+// host pointers, one device, `count` elements starting at the given pointers
+int modexp_host_shard(Op& op, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
+                      int mod_words, int exp_words, size_t count, unsigned flags,
+                      int exp_bits, const std::vector<uint8_t>* sched, uint32_t* out) {
   const int L = class_words(mod_words);
-  if (!L) return fail(IPCLB200_ERR_UNSUPPORTED, "modulus wider than 8192 bits");
-  cudaStream_t s = g_ctx.stream;
+  cudaStream_t s = op.s;
   const bool sh_mod = flags & IPCLB200_SHARED_MOD;
   const bool sh_base = flags & IPCLB200_SHARED_BASE;
   const bool sh_exp = flags & IPCLB200_SHARED_EXP;
   ModexpParams p{};
   p.count = count;
   p.exp_words = exp_words;
-  p.exp_bits = max_bits(exp, exp_words, sh_exp ? 1 : count, exp_words);
+  p.exp_bits = exp_bits;
   std::shared_ptr<DevModulus> dm;
-  uint32_t* d_n0 = nullptr;
   if (sh_mod) {
     Limbs n;
     TRY(check_modulus(mod, mod_words, &n));
-    TRY(make_modulus(n, L, &dm));
+    TRY(make_modulus(op.dev, n, L, &dm));
+    CUDA_TRY(cudaSetDevice(op.dev->id));
     p.n = dm->mc.n;
     p.rr = dm->mc.rr;
     p.one = dm->mc.one;
@@ -684,11 +702,11 @@ int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
       memcpy(&hone[i * (size_t)L], h.one.data(), (size_t)L * 4);
       hn0[i] = h.n0inv;
     }
-    uint32_t *dn, *drr, *done;
-    TRY(scratch_get(3, count * (size_t)L, &dn));
-    TRY(scratch_get(4, count * (size_t)L, &drr));
-    TRY(scratch_get(6, count * (size_t)L, &done));
-    TRY(scratch_get(5, count, &d_n0));
+    uint32_t *dn, *drr, *done, *d_n0;
+    TRY(op.words(count * (size_t)L, &dn));
+    TRY(op.words(count * (size_t)L, &drr));
+    TRY(op.words(count * (size_t)L, &done));
+    TRY(op.words(count, &d_n0));
     CUDA_TRY(cudaMemcpyAsync(dn, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(drr, hrr.data(), hrr.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(done, hone.data(), hone.size() * 4, cudaMemcpyHostToDevice, s));
@@ -702,9 +720,9 @@ int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
     p.n0_stride = 1;
   }
   uint32_t *d_base, *d_exp, *d_out;
-  TRY(scratch_get(0, (sh_base ? 1 : count) * (size_t)L, &d_base));
-  TRY(scratch_get(1, (sh_exp ? 1 : count) * (size_t)exp_words, &d_exp));
-  TRY(scratch_get(2, count * (size_t)L, &d_out));
+  TRY(op.words((sh_base ? 1 : count) * (size_t)L, &d_base));
+  TRY(op.words((sh_exp ? 1 : count) * (size_t)exp_words, &d_exp));
+  TRY(op.words(count * (size_t)L, &d_out));
   TRY(upload_padded(d_base, base, mod_words, L, sh_base ? 1 : count, s));
   CUDA_TRY(cudaMemcpyAsync(d_exp, exp, (sh_exp ? 1 : count) * (size_t)exp_words * 4,
                            cudaMemcpyHostToDevice, s));
@@ -713,27 +731,20 @@ int modexp_host_impl(const uint32_t* base, const uint32_t* exp,
   p.exp = d_exp;
   p.exp_stride = sh_exp ? 0 : exp_words;
   p.out = d_out;
-  if (sh_exp && count >= 64 && p.exp_bits > 64) {
-    // one exponent for the whole batch (ct * scalar, ipcl/ciphertext.cpp:97-99;
-    // Miller-Rabin rounds): sliding-window schedule instead of scanning
-    const char* ns = getenv("IPCLB200_NO_SCHED");
-    if (!(ns && ns[0] == '1')) {
-      std::vector<uint8_t> sc = build_schedule(hbn::from_words(exp, exp_words), kSchedWindow);
-      uint32_t* d_sc;
-      TRY(scratch_get(8, (sc.size() + 3) / 4, &d_sc));
-      CUDA_TRY(cudaMemcpyAsync(d_sc, sc.data(), sc.size(), cudaMemcpyHostToDevice, s));
-      CUDA_TRY(cudaStreamSynchronize(s));  // sc dies at scope end
-      p.sched = reinterpret_cast<const uint8_t*>(d_sc);
-    }
+  if (sched) {
+    uint32_t* d_sc;
+    TRY(op.words((sched->size() + 3) / 4, &d_sc));
+    CUDA_TRY(cudaMemcpyAsync(d_sc, sched->data(), sched->size(), cudaMemcpyHostToDevice, s));
+    p.sched = reinterpret_cast<const uint8_t*>(d_sc);
   }
-  TRY(launch_modexp(p, L, s));
+  TRY(launch_modexp(op, p, L));
   TRY(download_padded(out, d_out, mod_words, L, count, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
   return 0;
 }
 
-int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
-                  Limbs* out) {
+// single modexp on the primary device through the batch kernel (key-setup
+// scalars: what the reference routes to ippSBModExp, ipcl/mod_exp.cpp:535-585)
+int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod, Limbs* out) {
   int mw = (int)mod.size();
   int ew = e.empty() ? 1 : (int)e.size();
   std::vector<uint32_t> b(mw), x(ew), m(mw), r(mw);
@@ -741,91 +752,175 @@ int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod,
   hbn::to_words(br, b.data(), mw);
   hbn::to_words(e, x.data(), ew);
   hbn::to_words(mod, m.data(), mw);
-  TRY(modexp_host_impl(b.data(), x.data(), m.data(), mw, ew, 1,
-                       IPCLB200_SHARED_MOD, r.data()));
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  Op op;
+  TRY(op.open(dev));
+  TRY(modexp_host_shard(op, b.data(), x.data(), m.data(), mw, ew, 1, IPCLB200_SHARED_MOD,
+                        max_bits(x.data(), ew, 1, ew), nullptr, r.data()));
+  TRY(op.sync());
   *out = hbn::from_words(r.data(), mw);
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// fixed-base comb table of a DJN key (K5)
+// ---------------------------------------------------------------------------
+constexpr int kStarterWindow = 8;
+
+size_t comb_table_words(int L, int bits, int w) {
+  return (size_t)((bits + w - 1) / w) * ((size_t)L << w);
+}
+
+// enqueue the build of a table for `bits`-bit exponents on stream s.
 // small = true: the starter table (8-bit windows, 17 MB at a 2048-bit key);
-// false: the widest table the budget allows
-int build_comb(const ipclb200_pubkey* pk, int bits, bool small, cudaStream_t s) {
+// false: the widest table the key's budget allows.
+int build_comb(const ipclb200_pubkey* pk, PubDev* pd, int bits, bool small, cudaStream_t s,
+               CombTable* out) {
   const int L = pk->L;
-  constexpr int kStarterWindow = 8;
-  if (pk->d_comb && pk->comb_windows * pk->comb_w >= bits && (small || pk->comb_full))
-    return 0;
   // Widest window (<= 16 bits) whose table fits the budget.  B200 has 180 GB of
   // HBM and the kernel needs one 4L-byte entry per window and element, so the
   // table can be large: 1024-bit r at a 2048-bit key, w = 16 -> 64 windows x
   // 65536 entries x 512 B = 2.1 GB and 64 multiplies per encryption.
-  // Measured on B200, ms per 65536 encryptions: w = 8/9/10/11 -> 40.4/36.0/
-  // 32.6/30.1 (static split); see DESIGN.md for the wider ones.
-  size_t budget_mb = 4096;
+  size_t budget_mb = pk->comb_max_mb;
   if (const char* e = getenv("IPCLB200_COMB_MAX_MB")) budget_mb = strtoul(e, nullptr, 10);
   int w = 16;
-  auto table_words = [&](int ww) {
-    return (size_t)((bits + ww - 1) / ww) * ((size_t)L << ww);
-  };
-  while (w > 4 && table_words(w) * 4 > (budget_mb << 20)) w--;
+  while (w > 4 && comb_table_words(L, bits, w) * 4 > (budget_mb << 20)) w--;
   if (small && w > kStarterWindow) w = kStarterWindow;
   if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
     int v = atoi(cw);
     if (v >= 1 && v <= 16) w = v;
   }
-  if (pk->d_comb) {
-    // a wider exponent than the table covers: rebuild
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaFree(pk->d_comb));
-    pk->d_comb = nullptr;
-    pk->comb_windows = 0;
-  }
+  CombTable t;
   // back off to narrower windows if the allocation does not fit
   for (;; w--) {
-    cudaError_t e = cudaMalloc(&pk->d_comb, table_words(w) * sizeof(uint32_t));
+    cudaError_t e = cudaMalloc(&t.d, comb_table_words(L, bits, w) * sizeof(uint32_t));
     if (e == cudaSuccess) break;
     cudaGetLastError();
-    pk->d_comb = nullptr;
+    t.d = nullptr;
     if (w <= 4) return fail(IPCLB200_ERR_CUDA, "cannot allocate the fixed-base table");
   }
   int windows = (bits + w - 1) / w;
   if (windows < 1) windows = 1;
   CombParams cp{};
-  cp.m = pk->msq->mc;
-  cp.hs_m = pk->d_const + L;
-  cp.comb = pk->d_comb;
+  cp.m = pd->msq->mc;
+  cp.hs_m = pd->d_const + L;
+  cp.comb = t.d;
   cp.w = w;
   cp.w_lo = w > 11 ? (w + 1) / 2 : w;  // two-level build for wide windows
   cp.windows = windows;
   const int nchains = cp.w_lo < w ? 2 * windows : windows;
-#define F(K_, T_)                                                       \
-  {                                                                     \
-    comb_spine_kernel<K_, T_><<<1, 32, 0, s>>>(cp);                     \
-    int gpb = kBlockThreads / T_;                                       \
-    int grid = (nchains + gpb - 1) / gpb;                               \
-    comb_fill_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(cp);        \
-    if (cp.w_lo < w) {                                                  \
-      int eg = 0;                                                       \
-      TRY(grid_for(comb_expand_kernel<K_, T_>,                          \
-                   (size_t)windows << w, T_, &eg));                     \
-      comb_expand_kernel<K_, T_><<<eg, kBlockThreads, 0, s>>>(cp);      \
-      g_ctx.launches++;                                                 \
-    }                                                                   \
+#define F(K_, T_)                                                            \
+  {                                                                          \
+    comb_spine_kernel<K_, T_><<<1, 32, 0, s>>>(cp);                          \
+    int gpb = kBlockThreads / T_;                                            \
+    int grid = (nchains + gpb - 1) / gpb;                                    \
+    comb_fill_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(cp);             \
+    if (cp.w_lo < w) {                                                       \
+      int eg = 0;                                                            \
+      TRY(grid_for(pd->dev, comb_expand_kernel<K_, T_>, (size_t)windows << w, \
+                   T_, 0, &eg));                                             \
+      comb_expand_kernel<K_, T_><<<eg, kBlockThreads, 0, s>>>(cp);           \
+      g.launches++;                                                          \
+    }                                                                        \
   }
   IPCLB200_DISPATCH(L, F)
 #undef F
-  g_ctx.launches += 2;
+  g.launches += 2;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s));  // one-off; later users may be on other streams
-  pk->comb_w = w;
-  pk->comb_windows = windows;
-  pk->comb_full = !small;
+  CUDA_TRY(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(t.ready, s));
+  t.w = w;
+  t.windows = windows;
+  t.full = !small;
+  t.bytes = comb_table_words(L, bits, w) * sizeof(uint32_t);
+  if (t.full) {
+    std::lock_guard<std::mutex> lk(pd->dev->mu);
+    pd->dev->comb_bytes += t.bytes;
+  }
+  *out = t;
   return 0;
 }
 
-int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
-                     int pt_words, const uint32_t* d_r, int r_words,
-                     int r_bits, size_t count, int make_secure, uint32_t* d_ct,
-                     cudaStream_t s) {
+// The table this launch uses.  A key starts with the small table (built on the
+// caller's stream, a few ms) and, once it has encrypted `comb_upgrade_at`
+// elements, gets the wide one built on the device's side stream: encryptions
+// keep using the small table until the wide one is ready -- nobody waits for
+// the 35-50 ms build.  IPCLB200_COMB_SYNC=1 waits for it (benchmarks, tests).
+int comb_for_launch(const ipclb200_pubkey* pk_c, PubDev* pd, int bits, size_t count,
+                    cudaStream_t s, CombTable* use) {
+  ipclb200_pubkey* pk = const_cast<ipclb200_pubkey*>(pk_c);
+  std::lock_guard<std::mutex> lk(pk->mu);
+  pk->enc_total += count;
+  size_t upgrade_at = pk->comb_upgrade_at;
+  if (const char* e = getenv("IPCLB200_COMB_UPGRADE")) upgrade_at = strtoul(e, nullptr, 10);
+  const bool want_full = pk->enc_total >= upgrade_at;
+  const char* sync_env = getenv("IPCLB200_COMB_SYNC");
+  const bool sync_build = sync_env && sync_env[0] == '1';
+  // adopt a finished wide table
+  if (pd->next_pending) {
+    cudaError_t q = sync_build ? cudaEventSynchronize(pd->next.ready)
+                               : cudaEventQuery(pd->next.ready);
+    if (q == cudaSuccess) {
+      if (pd->cur.d) pd->retired.push_back(pd->cur);
+      pd->cur = pd->next;
+      pd->next = CombTable{};
+      pd->next_pending = false;
+    } else if (q != cudaErrorNotReady) {
+      return fail(IPCLB200_ERR_CUDA, std::string("comb build: ") + cudaGetErrorString(q));
+    }
+    cudaGetLastError();
+  }
+  const bool covers = pd->cur.d && pd->cur.w * pd->cur.windows >= bits;
+  if (!covers) {
+    // first use, or a wider exponent than the table covers: build on the caller's
+    // stream (ordered before the kernel that needs it)
+    if (pd->cur.d) pd->retired.push_back(pd->cur);
+    pd->cur = CombTable{};
+    if (pd->next_pending && pd->next.w * pd->next.windows < bits) {
+      cudaEventSynchronize(pd->next.ready);
+      pd->retired.push_back(pd->next);
+      pd->next = CombTable{};
+      pd->next_pending = false;
+    }
+    TRY(build_comb(pk, pd, bits, true, s, &pd->cur));
+  }
+  if (want_full && !pd->cur.full && !pd->next_pending) {
+    // device-wide budget for wide tables: past it the key stays on its small table
+    size_t budget_mb = 65536;
+    if (const char* e = getenv("IPCLB200_COMB_DEVICE_MB")) budget_mb = strtoul(e, nullptr, 10);
+    size_t alive;
+    {
+      std::lock_guard<std::mutex> dl(pd->dev->mu);
+      alive = pd->dev->comb_bytes;
+    }
+    const int tbits = std::max(bits, pk->rand_bits);
+    if (alive + comb_table_words(pk->L, tbits, 16) * 4 <= (budget_mb << 20)) {
+      // the side stream must see the constants the caller's stream may still be
+      // uploading: key blocks are uploaded synchronously, nothing to wait for
+      TRY(build_comb(pk, pd, tbits, false, pd->dev->side, &pd->next));
+      pd->next_pending = true;
+      if (sync_build) {
+        CUDA_TRY(cudaEventSynchronize(pd->next.ready));
+        if (pd->cur.d) pd->retired.push_back(pd->cur);
+        pd->cur = pd->next;
+        pd->next = CombTable{};
+        pd->next_pending = false;
+      }
+    }
+  }
+  // the launch stream waits for the build (no-op once it has completed)
+  CUDA_TRY(cudaStreamWaitEvent(s, pd->cur.ready, 0));
+  *use = pd->cur;
+  return 0;
+}
+
+int encrypt_dev_impl(Op& op, const ipclb200_pubkey* pk, const uint32_t* d_pt, int pt_words,
+                     const uint32_t* d_r, int r_words, int r_bits, size_t count,
+                     int make_secure, uint32_t* d_ct) {
+  PubDev* pd = nullptr;
+  TRY(pub_dev(pk, op.dev, &pd));
+  CUDA_TRY(cudaSetDevice(op.dev->id));
   const int L = pk->L;
   EncryptParams p{};
   p.pt = d_pt;
@@ -833,10 +928,10 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   p.r = d_r;
   p.r_words = r_words;
   p.r_bits = r_bits;
-  p.m = pk->msq->mc;
-  p.nR = pk->d_const;
-  p.hs_m = pk->d_const + L;
-  p.n_exp = pk->d_const + 2 * L;
+  p.m = pd->msq->mc;
+  p.nR = pd->d_const;
+  p.hs_m = pd->d_const + L;
+  p.n_exp = pd->d_const + 2 * L;
   p.n_exp_words = pk->nl;
   p.ct = d_ct;
   p.count = count;
@@ -845,23 +940,15 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
     p.mode = 0;
   } else if (pk->djn) {
     const char* no_comb = getenv("IPCLB200_NO_COMB");
-    // DJN: fixed-base comb (built on first use, ~20 ms and up to 160 MB per
-    // key; IPCLB200_NO_COMB=1 keeps the generic windowed path instead)
+    // DJN: fixed-base comb (IPCLB200_NO_COMB=1 keeps the generic windowed path)
     if (!(no_comb && no_comb[0] == '1')) {
-      // a key starts with a small table (8-bit windows: 17 MB and ~130 products
-      // per encryption at a 2048-bit key) and moves to the widest one the budget
-      // allows (16-bit windows, 2.1 GB, 66 products) once it has encrypted
-      // IPCLB200_COMB_UPGRADE (default 8192) elements: a key that is used a few
-      // times does not pay for 2 GB of HBM
-      size_t upgrade_at = 8192;
-      if (const char* e = getenv("IPCLB200_COMB_UPGRADE")) upgrade_at = strtoul(e, nullptr, 10);
-      pk->enc_total += count;
-      TRY(build_comb(pk, r_bits > pk->rand_bits ? r_bits : pk->rand_bits,
-                     pk->enc_total < upgrade_at, s));
+      CombTable t;
+      TRY(comb_for_launch(pk, pd, r_bits > pk->rand_bits ? r_bits : pk->rand_bits, count,
+                          op.s, &t));
       p.mode = 1;
-      p.comb = pk->d_comb;
-      p.comb_w = pk->comb_w;
-      p.comb_windows = (r_bits + pk->comb_w - 1) / pk->comb_w;
+      p.comb = t.d;
+      p.comb_w = t.w;
+      p.comb_windows = (r_bits + t.w - 1) / t.w;
       if (p.comb_windows < 1) p.comb_windows = 1;
     } else {
       p.mode = 2;
@@ -870,21 +957,21 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   } else {
     p.mode = 3;
     const char* ns = getenv("IPCLB200_NO_SCHED");
-    if (pk->d_sched_n && !(ns && ns[0] == '1')) {
-      p.sched_n = pk->d_sched_n;
+    if (pd->d_sched_n && !(ns && ns[0] == '1')) {
+      p.sched_n = pd->d_sched_n;
       p.window = kSchedWindow - 1;
     } else {
       p.window = pick_window(pk->nl * 32);
     }
   }
   int grid = 0;
-#define F(K_, T_)                                                          \
-  {                                                                        \
-    TRY(grid_for(encrypt_kernel<K_, T_>, count, T_, &grid));               \
-    size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
-    TRY(table_ws_with_counter(s, groups * ((size_t)L << p.window),         \
-                              &p.table_ws, &p.work_counter));              \
-    encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);              \
+#define F(K_, T_)                                                             \
+  {                                                                           \
+    TRY(grid_for(op.dev, encrypt_kernel<K_, T_>, count, T_, 0, &grid));       \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                      \
+    TRY(table_ws(op, groups * ((size_t)L << p.window), &p.table_ws,           \
+                 &p.work_counter));                                           \
+    encrypt_kernel<K_, T_><<<grid, kBlockThreads, 0, op.s>>>(p);              \
   }
   switch (pick_layout(count, L)) {
     case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
@@ -892,51 +979,78 @@ int encrypt_dev_impl(const ipclb200_pubkey* pk, const uint32_t* d_pt,
     default: IPCLB200_DISPATCH(L, F)
   }
 #undef F
-  g_ctx.launches++;
+  g.launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-// CRT decrypt in two-digit arithmetic (decrypt_hensel_kernel + crt_combine_kernel).
-// d_x: count x 2*pl words (mp | mq per ciphertext).
-int decrypt_hensel_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
-                        size_t count, uint32_t* d_pt, uint32_t* d_x,
-                        cudaStream_t s) {
+// ---------------------------------------------------------------------------
+// decrypt
+// ---------------------------------------------------------------------------
+struct PrivPtrs {
+  const uint32_t *p, *q, *hpR, *hqR, *pinvR, *n, *muR, *lambda;
+  const uint8_t *sched_p, *sched_q, *sched_lambda;
+};
+PrivPtrs priv_ptrs(const ipclb200_privkey* sk, const PrivDev* sd) {
   const int pl = sk->pl;
+  const uint32_t* d = sd->d_const;
+  PrivPtrs r{};
+  r.p = d;
+  r.q = d + pl;
+  r.hpR = d + 4 * pl;
+  r.hqR = d + 5 * pl;
+  r.pinvR = d + 6 * pl;
+  r.n = d + 7 * pl;
+  r.muR = d + 9 * pl;
+  r.lambda = d + 11 * pl + 4;
+  r.sched_p = sd->d_sched;
+  r.sched_q = sd->d_sched + sk->off_sched_q;
+  r.sched_lambda = sd->d_sched + sk->off_sched_lambda;
+  return r;
+}
+
+// CRT decrypt in two-digit arithmetic (decrypt_hensel_kernel + crt_combine_kernel)
+int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
+                        const uint32_t* d_ct, size_t count, uint32_t* d_pt) {
+  const int pl = sk->pl;
+  const PrivPtrs pp = priv_ptrs(sk, sd);
+  uint32_t* d_mpq;
+  TRY(op.words(count * (size_t)(2 * pl), &d_mpq));
   DecryptHenselParams p{};
   p.ct = d_ct;
-  p.s0.blk = sk->d_hblk_p;
-  p.s0.sched = sk->d_hsched_p;
+  p.s0.blk = sd->d_hensel;
+  p.s0.sched = sd->d_hensel + sk->off_hsched_p;
   p.s0.n0inv = sk->p_n0inv;
-  p.s1.blk = sk->d_hblk_q;
-  p.s1.sched = sk->d_hsched_q;
+  p.s1.blk = sd->d_hensel + 10 * (size_t)pl;
+  p.s1.sched = sd->d_hensel + sk->off_hsched_q;
   p.s1.n0inv = sk->q_n0inv;
-  p.mpq = d_x;
+  p.mpq = d_mpq;
   p.count = count;
   p.table_entries = 1 << (kSchedWindow - 1);
-  // warps per SM: IPCLB200_HENSEL_BLOCKS blocks of 128 threads (default 3)
+  // blocks of 128 threads per SM: 3 (12 warps) saturate the multiplier pipe
+  // (measured: 1/2/3 blocks -> 139.6/97.0/92.4 ms per 65536 at a 2048-bit key)
   int want_blocks = 3;
   if (const char* e = getenv("IPCLB200_HENSEL_BLOCKS")) want_blocks = atoi(e);
   if (want_blocks < 1 || want_blocks > 4) want_blocks = 3;
 #define FH(K_, T_, MINB_, ROWS_)                                                        \
-  {                                                                                \
-    auto kern = decrypt_hensel_kernel<K_, T_, MINB_, ROWS_>;                          \
-    constexpr size_t smem = hensel_smem_bytes<K_, T_>(kBlockThreads);              \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                     \
-    int per_sm = 0;                                                                \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,          \
-                                                           kBlockThreads, smem));  \
+  {                                                                                     \
+    auto kern = decrypt_hensel_kernel<K_, T_, MINB_, ROWS_>;                            \
+    constexpr size_t smem = hensel_smem_bytes<K_, T_>(kBlockThreads);                   \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem));                                          \
+    int per_sm = 0;                                                                     \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, \
+                                                           smem));                      \
     if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "hensel kernel does not fit an SM"); \
-    if (per_sm > want_blocks) per_sm = want_blocks;                                \
-    const size_t gpb = kBlockThreads / T_;                                         \
-    const size_t chunks = 2 * ((count + (32 / T_) - 1) / (32 / T_));               \
-    const size_t need = (chunks + 3) / 4;                                          \
-    const size_t cap = (size_t)per_sm * g_ctx.sms;                                 \
-    const int grid = (int)(need < cap ? need : cap);                               \
-    TRY(table_ws_with_counter(s, (size_t)grid * gpb * 2 * pl * p.table_entries,    \
-                              &p.table_ws, &p.work_counter));                      \
-    kern<<<grid, kBlockThreads, smem, s>>>(p);                                     \
+    if (per_sm > want_blocks) per_sm = want_blocks;                                     \
+    const size_t gpb = kBlockThreads / T_;                                              \
+    const size_t chunks = 2 * ((count + (32 / T_) - 1) / (32 / T_));                    \
+    const size_t need = (chunks + 3) / 4;                                               \
+    const size_t cap = (size_t)per_sm * op.dev->sms;                                    \
+    const int grid = (int)(need < cap ? need : cap);                                    \
+    TRY(table_ws(op, (size_t)grid * gpb * 2 * pl * p.table_entries, &p.table_ws,        \
+                 &p.work_counter));                                                     \
+    kern<<<grid, kBlockThreads, smem, op.s>>>(p);                                       \
   }
   int rows = 8;
   if (const char* e = getenv("IPCLB200_HENSEL_ROWS")) rows = atoi(e);
@@ -950,317 +1064,98 @@ int decrypt_hensel_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel: unsupported prime width");
   }
 #undef FH
-  g_ctx.launches++;
+  g.launches++;
   CUDA_TRY(cudaGetLastError());
   CrtCombineParams f{};
-  f.mpq = d_x;
-  f.p = sk->d_p;
-  f.q = sk->d_q;
-  f.pinvR = sk->d_pinvR;
+  f.mpq = d_mpq;
+  f.p = pp.p;
+  f.q = pp.q;
+  f.pinvR = pp.pinvR;
   f.q_n0inv = sk->q_n0inv;
   f.pl = pl;
   f.pt = d_pt;
   f.count = count;
-  crt_combine_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
-  g_ctx.launches++;
+  crt_combine_kernel<<<(unsigned)((count + 63) / 64), 64, 0, op.s>>>(f);
+  g.launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
-                     size_t count, int use_crt, uint32_t* d_pt,
-                     uint32_t* d_x /* count x 4*pl words scratch */,
-                     cudaStream_t s) {
-  const int pl = sk->pl;
-  // the thread-per-integer kernel (mont_tile.cuh) does 15 % fewer multiplies
-  // but measured slower on B200 (194 ms vs 165 ms per 65536 at a 2048-bit
-  // key: only 8 warps/SM fit its shared-memory columns and it issues 2.7
-  // instructions per multiply); it stays opt-in
-  const char* force = getenv("IPCLB200_DECRYPT");
-  // default: two-digit (Hensel) arithmetic, half the multiplies of the generic
-  // kernel; IPCLB200_DECRYPT=int keeps the full-width kernel
-  if (use_crt && sk->hensel_ok && (!force || !strcmp(force, "hensel")))
-    return decrypt_hensel_impl(sk, d_ct, count, d_pt, d_x, s);
+}  // namespace
+
 #ifdef IPCLB200_EXPERIMENTS
-  const bool tile = force && !strcmp(force, "tile");
-  if (use_crt && tile && (sk->L == 32 || sk->L == 48 || sk->L == 64)) {
-    const int L = sk->L;
-    DecryptTileParams p{};
-    p.ct = d_ct;
-    p.m0 = sk->mp2->mc;
-    p.m1 = sk->mq2->mc;
-    p.ninv0_lo = make_uint4(sk->ninv_p[0], sk->ninv_p[1], sk->ninv_p[2], sk->ninv_p[3]);
-    p.ninv0_hi = make_uint4(sk->ninv_p[4], sk->ninv_p[5], sk->ninv_p[6], sk->ninv_p[7]);
-    p.ninv1_lo = make_uint4(sk->ninv_q[0], sk->ninv_q[1], sk->ninv_q[2], sk->ninv_q[3]);
-    p.ninv1_hi = make_uint4(sk->ninv_q[4], sk->ninv_q[5], sk->ninv_q[6], sk->ninv_q[7]);
-    p.prog0 = sk->d_prog_p;
-    p.prog1 = sk->d_prog_q;
-    p.x = d_x;
-    p.count = count;
-    p.slots = sk->tile_slots;
-    constexpr int NT = 128;
-    const int V = L / 4;
-    const size_t smem = (size_t)(2 * V * NT + 4 * V) * 16;
-    int grid = 0;
-#define FT(NB_)                                                                   \
+#include "experiments/host_exp.inc"
+#endif
+
+namespace {
+
+// full-width CRT modexps: x[i] = (ct^(p-1) mod p^2, ct^(q-1) mod q^2), L words each
+int crt_residues_impl(Op& op, const ipclb200_privkey* sk, PrivDev* sd, const uint32_t* d_ct,
+                      size_t count, uint32_t* d_x) {
+  const int L = sk->L;
+  const PrivPtrs pp = priv_ptrs(sk, sd);
+  DecryptCrtParams p{};
+  p.ct = d_ct;
+  p.m0 = sd->mp2->mc;
+  p.m1 = sd->mq2->mc;
+  p.sched0 = pp.sched_p;
+  p.sched1 = pp.sched_q;
+  p.x = d_x;
+  p.count = count;
+  p.table_entries = 1 << (kSchedWindow - 1);
+#ifdef IPCLB200_EXPERIMENTS
+  {
+    bool handled = false;
+    TRY(decrypt_crt_experiment(op, sk, sd, p, getenv("IPCLB200_DECRYPT"), &handled));
+    if (handled) return 0;
+  }
+#endif
+  int grid = 0;
+#define F(K_, T_)                                                                 \
   {                                                                               \
-    auto kern = decrypt_tile_kernel<NB_, NT>;                                     \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                    \
-    int per_sm = 0;                                                               \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem)); \
-    if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "tile kernel does not fit an SM"); \
-    size_t need = (2 * ((count + 31) / 32) + NT / 32 - 1) / (NT / 32);            \
-    size_t cap = (size_t)per_sm * g_ctx.sms;                                      \
-    grid = (int)(need < cap ? need : cap);                                        \
-    size_t ws_words = (size_t)grid * (NT / 32) * p.slots * V * 32 * 4 + 4;        \
-    uint32_t* ws = nullptr;                                                       \
-    TRY(table_ws_get((void*)s, ws_words, &ws));                                   \
-    p.table_ws = reinterpret_cast<uint4*>(ws);                                    \
-    p.work_counter = ws + (ws_words - 4);                                         \
-    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, 16, s));                          \
-    kern<<<grid, NT, smem, s>>>(p);                                               \
+    TRY(grid_for(op.dev, decrypt_crt_kernel<K_, T_>, 2 * count, T_, 0, &grid));   \
+    size_t groups = (size_t)grid * (kBlockThreads / T_);                          \
+    TRY(table_ws(op, groups * ((size_t)L * p.table_entries), &p.table_ws,         \
+                 &p.work_counter));                                               \
+    decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, op.s>>>(p);              \
   }
-    if (L == 32) FT(4) else if (L == 48) FT(6) else FT(8)
-#undef FT
-    CrtFinishParams f{};
-    f.x = d_x;
-    f.p = sk->d_p;
-    f.q = sk->d_q;
-    f.hpR = sk->d_hpR;
-    f.hqR = sk->d_hqR;
-    f.pinvR = sk->d_pinvR;
-    f.p_inv32 = sk->p_inv32;
-    f.q_inv32 = sk->q_inv32;
-    f.p_n0inv = sk->p_n0inv;
-    f.q_n0inv = sk->q_n0inv;
-    f.pl = pl;
-    f.xl = L;
-    f.pt = d_pt;
-    f.count = count;
-    crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
-    g_ctx.launches += 2;
-    CUDA_TRY(cudaGetLastError());
-  } else
-#endif
-  if (use_crt) {
-    const int L = sk->L;
-    DecryptCrtParams p{};
-    p.ct = d_ct;
-    p.m0 = sk->mp2->mc;
-    p.m1 = sk->mq2->mc;
-    p.sched0 = sk->d_sched_p;
-    p.sched1 = sk->d_sched_q;
-    p.x = d_x;
-    p.count = count;
-    p.table_entries = 1 << (kSchedWindow - 1);
-    // which pipes: "int" = integer kernel only, "fp" = FP64 kernel only,
-    // "dual" = both roles in one kernel, "dual2" = two kernels on two streams
-    // sharing the work counter.  FP64 needs the 64-word class (2048-bit key).
-#ifdef IPCLB200_EXPERIMENTS
-    const char* mode = force ? force : "int";
-    const bool want_fp = !strcmp(mode, "fp"), want_dual = !strcmp(mode, "dual"),
-               want_dual2 = !strcmp(mode, "dual2"), want_sqr = !strcmp(mode, "sqr");
-    if ((!strcmp(mode, "k32s") || !strcmp(mode, "k32s2")) && L == 64) {
-      // 32 x 2 layout, multiplier rows from shared memory; 3 (or 2) blocks per SM
-      const bool three = !strcmp(mode, "k32s");
-      const size_t smem = (size_t)(kBlockThreads / 2) * kSbGroupWords * sizeof(uint32_t);
-      int per_sm = 0;
-      if (three)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, decrypt_crt_k32s_kernel<3>, kBlockThreads, smem));
-      else
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, decrypt_crt_k32s_kernel<2>, kBlockThreads, smem));
-      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "k32s kernel does not fit an SM");
-      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
-      const size_t capb = (size_t)per_sm * g_ctx.sms;
-      const int grid = (int)(need < capb ? need : capb);
-      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
-                                &p.work_counter));
-      if (three)
-        decrypt_crt_k32s_kernel<3><<<grid, kBlockThreads, smem, s>>>(p);
-      else
-        decrypt_crt_k32s_kernel<2><<<grid, kBlockThreads, smem, s>>>(p);
-      g_ctx.launches++;
-      CUDA_TRY(cudaGetLastError());
-    } else if (!strcmp(mode, "sqr2") && L == 64 && pick_layout(2 * count, L) == 0) {
-      // symmetric squarings in the 32 x 2 layout (MontSqr2)
-      constexpr size_t smem = sqr2_smem_bytes(kBlockThreads);
-      static bool attr_set2 = false;
-      if (!attr_set2) {
-        CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_sqr2_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set2 = true;
-      }
-      int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_sqr2_kernel,
-                                                             kBlockThreads, smem));
-      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "sqr2 kernel does not fit an SM");
-      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
-      const size_t capb = (size_t)per_sm * g_ctx.sms;
-      const int grid = (int)(need < capb ? need : capb);
-      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
-                                &p.work_counter));
-      decrypt_crt_sqr2_kernel<<<grid, kBlockThreads, smem, s>>>(p);
-      g_ctx.launches++;
-      CUDA_TRY(cudaGetLastError());
-    } else if (!strcmp(mode, "k32") && L == 64) {
-      int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_k32_kernel,
-                                                             kBlockThreads, 0));
-      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "k32 kernel does not fit an SM");
-      const size_t need = (2 * ((count + 15) / 16) + 3) / 4;
-      const size_t capb = (size_t)per_sm * g_ctx.sms;
-      const int grid = (int)(need < capb ? need : capb);
-      TRY(table_ws_with_counter(s, (size_t)grid * 64 * L * p.table_entries, &p.table_ws,
-                                &p.work_counter));
-      decrypt_crt_k32_kernel<<<grid, kBlockThreads, 0, s>>>(p);
-      g_ctx.launches++;
-      CUDA_TRY(cudaGetLastError());
-    } else if (want_sqr && L == 64 && pick_layout(2 * count, L) == 0) {
-      // symmetric squarings (mont_sqr.cuh), 64-word class
-      constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
-      static bool attr_set = false;
-      if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_sqr_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
-      int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decrypt_crt_sqr_kernel,
-                                                             kBlockThreads, smem));
-      if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "sqr kernel does not fit an SM");
-      const size_t need = (2 * ((count + 7) / 8) + 3) / 4;
-      const size_t capb = (size_t)per_sm * g_ctx.sms;
-      const int grid = (int)(need < capb ? need : capb);
-      TRY(table_ws_with_counter(s, (size_t)grid * 32 * L * p.table_entries, &p.table_ws,
-                                &p.work_counter));
-      decrypt_crt_sqr_kernel<<<grid, kBlockThreads, smem, s>>>(p);
-      g_ctx.launches++;
-      CUDA_TRY(cudaGetLastError());
-    } else
-    if ((want_fp || want_dual || want_dual2) && sk->fp_ok && L == kFpWords) {
-      constexpr int FL = kFpLimbs;
-      constexpr size_t smem = fp_role_smem(kFpK, kFpT);
-      const int sms = g_ctx.sms;
-      const size_t chunks = 2 * ((count + 7) / 8);          // warps of work
-      const size_t need = (chunks + 3) / 4;                 // blocks of 4 warps
-      auto env_int = [](const char* name, int dflt) {
-        const char* e = getenv(name);
-        return e ? atoi(e) : dflt;
-      };
-      DecryptFpParams f{};
-      f.ct = d_ct;
-      f.f0 = sk->fp0;
-      f.f1 = sk->fp1;
-      f.sched0 = sk->d_sched_p;
-      f.sched1 = sk->d_sched_q;
-      f.x = d_x;
-      f.count = count;
-      f.table_entries = p.table_entries;
-      f.debug_stage = want_fp ? env_int("IPCLB200_FP_DEBUG_STAGE", 0) : 0;
-      auto cap = [&](int per_sm) {
-        size_t c = (size_t)per_sm * sms;
-        return (int)(need < c ? need : c);
-      };
-      if (want_fp) {
-        int blocks = env_int("IPCLB200_FP_BLOCKS", 2);
-        if (blocks < 1 || blocks > 3) blocks = 2;
-        const int grid = cap(blocks);
-        TRY(table_ws_with_counter(s, (size_t)grid * 32 * FL * f.table_entries,
-                                  &f.table_ws, &f.work_counter, 1));
-        if (blocks == 3)
-          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3><<<grid, kBlockThreads, smem, s>>>(f);
-        else
-          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 2><<<grid, kBlockThreads, smem, s>>>(f);
-        g_ctx.launches++;
-      } else if (want_dual) {
-        DecryptDualParams d{};
-        const int grid = cap(3);
-        TRY(table_ws_with_counter(s, (size_t)grid * 32 * L * p.table_entries,
-                                  &p.table_ws, &p.work_counter));
-        uint32_t* fws = nullptr;
-        const size_t fwords = (size_t)grid * 32 * FL * f.table_entries;
-        TRY(table_ws_get((void*)((uintptr_t)s + 1), fwords + 1024, &fws));
-        f.table_ws = fws;
-        f.work_counter = p.work_counter;
-        d.i = p;
-        d.f = f;
-        d.sm_slots = fws + fwords;
-        d.fp_mask = (unsigned)env_int("IPCLB200_FP_MASK", 4);
-        d.slots_per_sm = 3;
-        CUDA_TRY(cudaMemsetAsync(d.sm_slots, 0, 1024 * sizeof(uint32_t), s));
-        decrypt_crt_dual_kernel<16, 4, kFpK, kFpT><<<grid, kBlockThreads, smem, s>>>(d);
-        g_ctx.launches++;
-      } else {
-        int ib = 2, fb = 1;
-        if (const char* e = getenv("IPCLB200_DUAL2")) sscanf(e, "%d,%d", &ib, &fb);
-        if (ib < 0 || ib > 3) ib = 2;
-        if (fb < 0 || fb > 2 || (ib == 0 && fb == 0)) fb = 1;
-        const int igrid = cap(ib ? ib : 1), fgrid = cap(fb ? fb : 1);
-        TRY(table_ws_with_counter(s, (size_t)igrid * 32 * L * p.table_entries,
-                                  &p.table_ws, &p.work_counter));
-        uint32_t* fws = nullptr;
-        TRY(table_ws_get((void*)((uintptr_t)s + 1),
-                         (size_t)fgrid * 32 * FL * f.table_entries, &fws));
-        f.table_ws = fws;
-        f.work_counter = p.work_counter;
-        // kernels with different shared-memory carve-outs cannot share an SM:
-        // ask for the same one for both
-        static bool carve_set = false;
-        if (!carve_set) {
-          const int carve = env_int("IPCLB200_CARVEOUT", 100);
-          if (carve >= 0) {
-            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_kernel<16, 4>,
-                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_fp224_kernel<kFpK, kFpT, kFpWords>,
-                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            CUDA_TRY(cudaFuncSetAttribute(decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3>,
-                                          cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-          }
-          carve_set = true;
-        }
-        cudaStream_t s2 = g_ctx.aux_stream;
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_fork, s));
-        CUDA_TRY(cudaStreamWaitEvent(s2, g_ctx.ev_fork, 0));
-        if (ib) decrypt_crt_kernel<16, 4><<<igrid, kBlockThreads, 0, s>>>(p);
-        if (fb == 1)
-          decrypt_crt_fp224_kernel<kFpK, kFpT, kFpWords><<<fgrid, kBlockThreads, smem, s2>>>(f);
-        else if (fb == 2)
-          decrypt_crt_fp_kernel<kFpK, kFpT, kFpWords, 3><<<fgrid, kBlockThreads, smem, s2>>>(f);
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_join, s2));
-        CUDA_TRY(cudaStreamWaitEvent(s, g_ctx.ev_join, 0));
-        g_ctx.launches += 2;
-      }
-      CUDA_TRY(cudaGetLastError());
-    } else
-#endif
-    {
-      int grid = 0;
-#define F(K_, T_)                                                          \
-  {                                                                        \
-    TRY(grid_for(decrypt_crt_kernel<K_, T_>, 2 * count, T_, &grid));       \
-    size_t groups = (size_t)grid * (kBlockThreads / T_);                   \
-    TRY(table_ws_with_counter(s, groups * ((size_t)L * p.table_entries),   \
-                              &p.table_ws, &p.work_counter));              \
-    decrypt_crt_kernel<K_, T_><<<grid, kBlockThreads, 0, s>>>(p);          \
+  switch (pick_layout(2 * count, L)) {
+    case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
+    case 2: IPCLB200_DISPATCH_MID(L, F) break;
+    default: IPCLB200_DISPATCH(L, F)
   }
-      switch (pick_layout(2 * count, L)) {
-        case 1: IPCLB200_DISPATCH_WIDE(L, F) break;
-        case 2: IPCLB200_DISPATCH_MID(L, F) break;
-        default: IPCLB200_DISPATCH(L, F)
-      }
 #undef F
-      g_ctx.launches++;
-    }
+  g.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// d_ct: count x 4*pl words when the key widths are kernel size classes (the
+// *_dev contract), else count x 2L (CRT) / Lnsq (RAW) zero-padded words
+int decrypt_dev_impl(Op& op, const ipclb200_privkey* sk, const uint32_t* d_ct, size_t count,
+                     int use_crt, uint32_t* d_pt) {
+  PrivDev* sd = nullptr;
+  TRY(priv_dev(sk, op.dev, &sd));
+  CUDA_TRY(cudaSetDevice(op.dev->id));
+  const int pl = sk->pl;
+  const PrivPtrs pp = priv_ptrs(sk, sd);
+  const char* force = getenv("IPCLB200_DECRYPT");
+  if (use_crt) {
+    // default: two-digit (Hensel) arithmetic, half the multiplies of the
+    // full-width kernel; IPCLB200_DECRYPT=int keeps the full-width kernel
+    if (sk->hensel_ok && sk->L == 2 * pl && (!force || !strcmp(force, "hensel")))
+      return decrypt_hensel_impl(op, sk, sd, d_ct, count, d_pt);
+    const int L = sk->L;
+    uint32_t* d_x;
+    TRY(op.words(count * (size_t)(2 * L), &d_x));
+    TRY(crt_residues_impl(op, sk, sd, d_ct, count, d_x));
     CrtFinishParams f{};
     f.x = d_x;
-    f.p = sk->d_p;
-    f.q = sk->d_q;
-    f.hpR = sk->d_hpR;
-    f.hqR = sk->d_hqR;
-    f.pinvR = sk->d_pinvR;
+    f.p = pp.p;
+    f.q = pp.q;
+    f.hpR = pp.hpR;
+    f.hqR = pp.hqR;
+    f.pinvR = pp.pinvR;
     f.p_inv32 = sk->p_inv32;
     f.q_inv32 = sk->q_inv32;
     f.p_n0inv = sk->p_n0inv;
@@ -1269,46 +1164,155 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
     f.xl = L;
     f.pt = d_pt;
     f.count = count;
-    crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
-    g_ctx.launches++;
+    crt_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, op.s>>>(f);
+    g.launches++;
     CUDA_TRY(cudaGetLastError());
   } else {
-    const int L = sk->mnsq->L;
+    const int L = sk->Lnsq;
+    uint32_t* d_x;
+    TRY(op.words(count * (size_t)L, &d_x));
     ModexpParams p{};
     p.base = d_ct;
     p.base_stride = L;
-    p.exp = sk->d_lambda;
+    p.exp = pp.lambda;
     p.exp_stride = 0;
     p.exp_words = 2 * pl;
     p.exp_bits = sk->lambda_bits;
-    p.n = sk->mnsq->mc.n;
-    p.rr = sk->mnsq->mc.rr;
-    p.one = sk->mnsq->mc.one;
-    p.n0inv = sk->mnsq->d_n0inv;
+    p.n = sd->mnsq->mc.n;
+    p.rr = sd->mnsq->mc.rr;
+    p.one = sd->mnsq->mc.one;
+    p.n0inv = sd->mnsq->d_n0inv;
     p.mod_stride = 0;
     p.n0_stride = 0;
     p.out = d_x;
     p.count = count;
     {
       const char* ns = getenv("IPCLB200_NO_SCHED");
-      if (!(ns && ns[0] == '1')) p.sched = sk->d_sched_lambda;
+      if (!(ns && ns[0] == '1')) p.sched = pp.sched_lambda;
     }
-    TRY(launch_modexp(p, L, s));
+    TRY(launch_modexp(op, p, L));
     RawFinishParams f{};
     f.x = d_x;
-    f.n = sk->d_n;
-    f.muR = sk->d_muR;
+    f.n = pp.n;
+    f.muR = pp.muR;
     f.n_inv32 = sk->n_inv32;
     f.n_n0inv = sk->n_n0inv;
     f.nl = 2 * pl;
     f.xl = L;
     f.pt = d_pt;
     f.count = count;
-    raw_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, s>>>(f);
-    g_ctx.launches++;
+    raw_finish_kernel<<<(unsigned)((count + 63) / 64), 64, 0, op.s>>>(f);
+    g.launches++;
     CUDA_TRY(cudaGetLastError());
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// NCCL (loaded on first use: the library itself does not link against it)
+// ---------------------------------------------------------------------------
+struct Nccl {
+  typedef struct ncclComm* comm_t;
+  void* handle = nullptr;
+  bool tried = false;
+  int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::vector<int> ids;       // device ordinals of the communicator clique
+  std::vector<comm_t> comms;  // one per device, rank = index
+  std::mutex mu;
+};
+Nccl g_nccl;
+constexpr int kNcclUint32 = 3;  // ncclUint32 in nccl.h
+
+int nccl_load() {
+  if (g_nccl.tried)
+    return g_nccl.handle ? 0 : fail(IPCLB200_ERR_NCCL, "libnccl.so.2 not found");
+  g_nccl.tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) return fail(IPCLB200_ERR_NCCL, "libnccl.so.2 not found");
+#define SYM(field, name)                                            \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, name);            \
+  if (!g_nccl.field) {                                              \
+    g_nccl.handle = nullptr;                                        \
+    return fail(IPCLB200_ERR_NCCL, std::string("missing ") + name); \
+  }
+  SYM(CommInitAll, "ncclCommInitAll")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+
+#define NCCL_TRY(expr)                                                       \
+  do {                                                                       \
+    int r_ = (expr);                                                         \
+    if (r_ != 0)                                                             \
+      return fail(IPCLB200_ERR_NCCL,                                         \
+                  std::string(#expr) + ": " + g_nccl.GetErrorString(r_));    \
+  } while (0)
+
+// communicators over the devices of `shards` (rank = shard index)
+int nccl_comms(const std::vector<Shard>& shards) {
+  TRY(nccl_load());
+  std::vector<int> ids;
+  for (auto& sh : shards) ids.push_back(sh.dev->id);
+  if (ids == g_nccl.ids) return 0;
+  for (auto c : g_nccl.comms)
+    if (c) g_nccl.CommDestroy(c);
+  g_nccl.comms.assign(ids.size(), nullptr);
+  g_nccl.ids.clear();
+  NCCL_TRY(g_nccl.CommInitAll(g_nccl.comms.data(), (int)ids.size(), ids.data()));
+  g_nccl.ids = ids;
+  return 0;
+}
+
+}  // namespace
+
+// a batch of big integers sharded over the active devices
+struct ipclb200_batch {
+  size_t count = 0;
+  int words = 0;
+  std::vector<Shard> shards;
+  std::vector<uint32_t*> d;
+};
+
+namespace {
+
+bool same_plan(const ipclb200_batch* a, const ipclb200_batch* b) {
+  if (a->count != b->count || a->shards.size() != b->shards.size()) return false;
+  for (size_t i = 0; i < a->shards.size(); i++)
+    if (a->shards[i].dev != b->shards[i].dev || a->shards[i].begin != b->shards[i].begin ||
+        a->shards[i].count != b->shards[i].count)
+      return false;
+  return true;
+}
+
+int modmul_on(Op& op, const uint32_t* d_a, const uint32_t* d_b, const Limbs& n, int L,
+              size_t count, unsigned flags, uint32_t* d_out) {
+  std::shared_ptr<DevModulus> dm;
+  TRY(make_modulus(op.dev, n, L, &dm));
+  CUDA_TRY(cudaSetDevice(op.dev->id));
+  ModmulParams p{};
+  p.a = d_a;
+  p.b = d_b;
+  p.b_stride = (flags & IPCLB200_SHARED_B) ? 0 : L;
+  p.m = dm->mc;
+  p.out = d_out;
+  p.count = count;
+  return launch_modmul(op, p, L);
 }
 
 }  // namespace
@@ -1318,74 +1322,142 @@ int decrypt_dev_impl(const ipclb200_privkey* sk, const uint32_t* d_ct,
 // ===========================================================================
 extern "C" {
 
-const char* ipclb200_version(void) { return "ipcl_b200 0.1 (sm_100a)"; }
-const char* ipclb200_last_error(void) { return t_err.c_str(); }
+const char* ipclb200_version(void) { return "ipcl_b200 0.2 (sm_100a)"; }
+const char* ipclb200_last_error(void) { return last_error().c_str(); }
 
-int ipclb200_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-  return n;
+int ipclb200_has_experiments(void) {
+#ifdef IPCLB200_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
 }
 
+int ipclb200_device_count(void) { return device_count_raw(); }
+
 int ipclb200_init(int device) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.ready && (device < 0 || device == g_ctx.device)) return 0;
-  if (g_ctx.ready)
-    return fail(IPCLB200_ERR_BAD_ARG, "already initialised on another device");
-  if (device >= 0) {
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev)
-      return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
-    g_requested_device = device;
+  const int ndev = device_count_raw();
+  if (ndev == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (device >= 0) {
+      if (device >= ndev) return fail(IPCLB200_ERR_NO_DEVICE, "no such CUDA device");
+      if (g.active_set &&
+          std::find(g.active.begin(), g.active.end(), device) == g.active.end())
+        return fail(IPCLB200_ERR_BAD_ARG, "already initialised on another device");
+      if (!g.active_set) {
+        g.active = {device};
+        g.active_set = true;
+      }
+    }
   }
-  return ensure_init_locked();
+  Dev* d = nullptr;
+  return primary_device(&d);
+}
+
+int ipclb200_init_devices(int n_devices) {
+  const int ndev = device_count_raw();
+  if (ndev == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  if (n_devices <= 0 || n_devices > ndev) n_devices = ndev;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.active.clear();
+    for (int i = 0; i < n_devices; i++) g.active.push_back(i);
+    g.active_set = true;
+  }
+  DeviceGuard guard;
+  std::vector<Dev*> devs;
+  TRY(active_devices(&devs));
+  // peer access helps NCCL's P2P transport; failures are not fatal
+  for (Dev* a : devs)
+    for (Dev* b : devs)
+      if (a != b) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, a->id, b->id) == cudaSuccess && can) {
+          cudaSetDevice(a->id);
+          cudaDeviceEnablePeerAccess(b->id, 0);
+        }
+        cudaGetLastError();
+      }
+  return 0;
+}
+
+int ipclb200_active_devices(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  return g.active_set ? (int)g.active.size() : 0;
 }
 
 void ipclb200_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (!g_ctx.ready) return;
-  cudaSetDevice(g_ctx.device);
-  cudaDeviceSynchronize();
-  for (int i = 0; i < Ctx::kSlots; i++) {
-    if (g_ctx.scratch[i]) cudaFree(g_ctx.scratch[i]);
-    g_ctx.scratch[i] = nullptr;
-    g_ctx.scratch_words[i] = 0;
+  std::lock_guard<std::mutex> lk(g.mu);
+  {
+    std::lock_guard<std::mutex> nl(g_nccl.mu);
+    for (auto c : g_nccl.comms)
+      if (c) g_nccl.CommDestroy(c);
+    g_nccl.comms.clear();
+    g_nccl.ids.clear();
   }
-  for (auto& kv : g_ctx.table_ws)
-    if (kv.second.first) cudaFree(kv.second.first);
-  g_ctx.table_ws.clear();
-  g_ctx.mod_cache.clear();
-  if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-  g_ctx.stream = nullptr;
-  if (g_ctx.aux_stream) cudaStreamDestroy(g_ctx.aux_stream);
-  g_ctx.aux_stream = nullptr;
-  if (g_ctx.ev_fork) cudaEventDestroy(g_ctx.ev_fork);
-  if (g_ctx.ev_join) cudaEventDestroy(g_ctx.ev_join);
-  g_ctx.ev_fork = g_ctx.ev_join = nullptr;
-  g_ctx.ready = false;
+  for (auto& slot : g.dev) {
+    Dev* d = slot.load();
+    if (!d) continue;
+    cudaSetDevice(d->id);
+    cudaDeviceSynchronize();
+    d->mod_cache.clear();
+    for (cudaStream_t s : d->idle) cudaStreamDestroy(s);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->side) cudaStreamDestroy(d->side);
+    delete d;
+    slot.store(nullptr);
+  }
+  g.active.clear();
+  g.active_set = false;
 }
 
-uint64_t ipclb200_launch_count(void) { return g_ctx.launches.load(); }
+uint64_t ipclb200_launch_count(void) { return g.launches.load(); }
 
-int ipclb200_modexp(const uint32_t* base, const uint32_t* exp,
-                    const uint32_t* mod, int mod_words, int exp_words,
-                    size_t count, unsigned flags, uint32_t* out) {
-  if (!base || !exp || !mod || !out)
-    return fail(IPCLB200_ERR_BAD_ARG, "modexp: null pointer");
+// ---- modexp ---------------------------------------------------------------
+int ipclb200_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
+                    int mod_words, int exp_words, size_t count, unsigned flags,
+                    uint32_t* out) {
+  if (!base || !exp || !mod || !out) return fail(IPCLB200_ERR_BAD_ARG, "modexp: null pointer");
   if (mod_words <= 0 || exp_words <= 0)
     return fail(IPCLB200_ERR_BAD_ARG, "modexp: non-positive width");
   if (mod_words > IPCLB200_MAX_MOD_WORDS)
     return fail(IPCLB200_ERR_UNSUPPORTED, "modexp: modulus wider than 8192 bits");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  return modexp_host_impl(base, exp, mod, mod_words, exp_words, count, flags, out);
+  DeviceGuard guard;
+  const bool sh_mod = flags & IPCLB200_SHARED_MOD;
+  const bool sh_base = flags & IPCLB200_SHARED_BASE;
+  const bool sh_exp = flags & IPCLB200_SHARED_EXP;
+  std::vector<Shard> shards;
+  TRY(plan_shards(sh_mod ? count : 1, &shards));
+  if (!sh_mod) shards[0].count = count;  // heterogeneous moduli: one device
+  const int exp_bits = max_bits(exp, exp_words, sh_exp ? 1 : count, exp_words);
+  // one exponent for the whole batch (ct * scalar, ipcl/ciphertext.cpp:97-99;
+  // Miller-Rabin rounds): sliding-window schedule instead of scanning
+  std::vector<uint8_t> sched;
+  if (sh_exp && count >= 64 && exp_bits > 64) {
+    const char* ns = getenv("IPCLB200_NO_SCHED");
+    if (!(ns && ns[0] == '1'))
+      sched = build_schedule(hbn::from_words(exp, exp_words), kSchedWindow);
+  }
+  std::vector<Op> ops(shards.size());
+  for (size_t i = 0; i < shards.size(); i++) {
+    const Shard& sh = shards[i];
+    TRY(ops[i].open(sh.dev));
+    TRY(modexp_host_shard(ops[i], sh_base ? base : base + sh.begin * (size_t)mod_words,
+                          sh_exp ? exp : exp + sh.begin * (size_t)exp_words,
+                          sh_mod ? mod : mod + sh.begin * (size_t)mod_words, mod_words,
+                          exp_words, sh.count, flags, exp_bits,
+                          sched.empty() ? nullptr : &sched,
+                          out + sh.begin * (size_t)mod_words));
+  }
+  for (auto& op : ops) TRY(op.sync());
+  return 0;
 }
 
-int ipclb200_modexp_dev(const uint32_t* d_base, const uint32_t* d_exp,
-                        const uint32_t* h_mod, int mod_words, int exp_words,
-                        int exp_bits, size_t count, unsigned flags,
-                        uint32_t* d_out, void* stream) {
+int ipclb200_modexp_dev(const uint32_t* d_base, const uint32_t* d_exp, const uint32_t* h_mod,
+                        int mod_words, int exp_words, int exp_bits, size_t count,
+                        unsigned flags, uint32_t* d_out, void* stream) {
   if (!d_base || !d_exp || !h_mod || !d_out)
     return fail(IPCLB200_ERR_BAD_ARG, "modexp_dev: null pointer");
   if (!(flags & IPCLB200_SHARED_MOD))
@@ -1394,145 +1466,127 @@ int ipclb200_modexp_dev(const uint32_t* d_base, const uint32_t* d_exp,
     return fail(IPCLB200_ERR_UNSUPPORTED,
                 "modexp_dev: mod_words must be one of 16,32,48,64,96,128,192,256");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_out, &dev));
   Limbs n;
   TRY(check_modulus(h_mod, mod_words, &n));
-  std::shared_ptr<DevModulus> dm;
-  TRY(make_modulus(n, mod_words, &dm));
-  cudaStream_t s = (cudaStream_t)stream;
-  ModexpParams p{};
-  p.base = d_base;
-  p.base_stride = (flags & IPCLB200_SHARED_BASE) ? 0 : mod_words;
-  p.exp = d_exp;
-  p.exp_stride = (flags & IPCLB200_SHARED_EXP) ? 0 : exp_words;
-  p.exp_words = exp_words;
-  p.exp_bits = exp_bits > 0 ? exp_bits : exp_words * 32;
-  p.n = dm->mc.n;
-  p.rr = dm->mc.rr;
-  p.one = dm->mc.one;
-  p.n0inv = dm->d_n0inv;
-  p.out = d_out;
-  p.count = count;
-  return launch_modexp(p, mod_words, s);
+  Op op;
+  TRY(op.open_on(dev, (cudaStream_t)stream));
+  return modexp_shared_dev(op, d_base, d_exp, n, mod_words, exp_words, exp_bits, count, flags,
+                           nullptr, d_out);
 }
 
-static int modmul_common(const uint32_t* d_a, const uint32_t* d_b,
-                         const Limbs& n, int L, size_t count, unsigned flags,
-                         uint32_t* d_out, cudaStream_t s) {
-  std::shared_ptr<DevModulus> dm;
-  TRY(make_modulus(n, L, &dm));
-  ModmulParams p{};
-  p.a = d_a;
-  p.b = d_b;
-  p.b_stride = (flags & IPCLB200_SHARED_B) ? 0 : L;
-  p.m = dm->mc;
-  p.out = d_out;
-  p.count = count;
-  return launch_modmul(p, L, s);
-}
-
-int ipclb200_modmul(const uint32_t* a, const uint32_t* b, const uint32_t* mod,
-                    int mod_words, size_t count, unsigned flags, uint32_t* out) {
-  if (!a || !b || !mod || !out)
-    return fail(IPCLB200_ERR_BAD_ARG, "modmul: null pointer");
+// ---- modmul -----------------------------------------------------------------
+int ipclb200_modmul(const uint32_t* a, const uint32_t* b, const uint32_t* mod, int mod_words,
+                    size_t count, unsigned flags, uint32_t* out) {
+  if (!a || !b || !mod || !out) return fail(IPCLB200_ERR_BAD_ARG, "modmul: null pointer");
   if (mod_words <= 0) return fail(IPCLB200_ERR_BAD_ARG, "modmul: non-positive width");
   const int L = class_words(mod_words);
   if (!L) return fail(IPCLB200_ERR_UNSUPPORTED, "modmul: modulus wider than 8192 bits");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
   Limbs n;
   TRY(check_modulus(mod, mod_words, &n));
-  cudaStream_t s = g_ctx.stream;
+  DeviceGuard guard;
   const bool sh_b = flags & IPCLB200_SHARED_B;
-  uint32_t *d_a, *d_b, *d_out;
-  TRY(scratch_get(0, count * (size_t)L, &d_a));
-  TRY(scratch_get(1, (sh_b ? 1 : count) * (size_t)L, &d_b));
-  TRY(scratch_get(2, count * (size_t)L, &d_out));
-  TRY(upload_padded(d_a, a, mod_words, L, count, s));
-  TRY(upload_padded(d_b, b, mod_words, L, sh_b ? 1 : count, s));
-  TRY(modmul_common(d_a, d_b, n, L, count, flags, d_out, s));
-  TRY(download_padded(out, d_out, mod_words, L, count, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  std::vector<Shard> shards;
+  TRY(plan_shards(count, &shards));
+  std::vector<Op> ops(shards.size());
+  for (size_t i = 0; i < shards.size(); i++) {
+    const Shard& sh = shards[i];
+    Op& op = ops[i];
+    TRY(op.open(sh.dev));
+    uint32_t *d_a, *d_b, *d_out;
+    TRY(op.words(sh.count * (size_t)L, &d_a));
+    TRY(op.words((sh_b ? 1 : sh.count) * (size_t)L, &d_b));
+    TRY(op.words(sh.count * (size_t)L, &d_out));
+    TRY(upload_padded(d_a, a + sh.begin * (size_t)mod_words, mod_words, L, sh.count, op.s));
+    TRY(upload_padded(d_b, sh_b ? b : b + sh.begin * (size_t)mod_words, mod_words, L,
+                      sh_b ? 1 : sh.count, op.s));
+    TRY(modmul_on(op, d_a, d_b, n, L, sh.count, flags, d_out));
+    TRY(download_padded(out + sh.begin * (size_t)mod_words, d_out, mod_words, L, sh.count,
+                        op.s));
+  }
+  for (auto& op : ops) TRY(op.sync());
   return 0;
 }
 
-int ipclb200_modmul_dev(const uint32_t* d_a, const uint32_t* d_b,
-                        const uint32_t* h_mod, int mod_words, size_t count,
-                        unsigned flags, uint32_t* d_out, void* stream) {
+int ipclb200_modmul_dev(const uint32_t* d_a, const uint32_t* d_b, const uint32_t* h_mod,
+                        int mod_words, size_t count, unsigned flags, uint32_t* d_out,
+                        void* stream) {
   if (!d_a || !d_b || !h_mod || !d_out)
     return fail(IPCLB200_ERR_BAD_ARG, "modmul_dev: null pointer");
   if (mod_words <= 0 || class_words(mod_words) != mod_words)
     return fail(IPCLB200_ERR_UNSUPPORTED,
                 "modmul_dev: mod_words must be one of 16,32,48,64,96,128,192,256");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_out, &dev));
   Limbs n;
   TRY(check_modulus(h_mod, mod_words, &n));
-  return modmul_common(d_a, d_b, n, mod_words, count, flags, d_out,
-                       (cudaStream_t)stream);
+  Op op;
+  TRY(op.open_on(dev, (cudaStream_t)stream));
+  return modmul_on(op, d_a, d_b, n, mod_words, count, flags, d_out);
 }
 
 // ---- public key -----------------------------------------------------------
-int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs,
-                           int rand_bits, ipclb200_pubkey** out) {
+int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs, int rand_bits,
+                           ipclb200_pubkey** out) {
   if (!n || !out || n_words <= 0)
     return fail(IPCLB200_ERR_BAD_ARG, "pubkey_create: bad argument");
   if (2 * n_words > IPCLB200_MAX_MOD_WORDS)
     return fail(IPCLB200_ERR_UNSUPPORTED, "pubkey_create: key wider than 4096 bits");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
+  if (device_count_raw() == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  DeviceGuard guard;
   std::unique_ptr<ipclb200_pubkey> pk(new ipclb200_pubkey);
   pk->nl = n_words;
   pk->n = hbn::from_words(n, n_words);
   if (pk->n.empty()) return fail(IPCLB200_ERR_BAD_ARG, "pubkey_create: n is zero");
-  if (!(pk->n[0] & 1u))
-    return fail(IPCLB200_ERR_EVEN_MODULUS, "pubkey_create: n is even");
+  if (!(pk->n[0] & 1u)) return fail(IPCLB200_ERR_EVEN_MODULUS, "pubkey_create: n is even");
   pk->nsq = hbn::mul(pk->n, pk->n);
   pk->L = class_words(2 * n_words);
   const int L = pk->L;
-  TRY(make_modulus(pk->nsq, L, &pk->msq));
-  // n*R mod n^2, n (exponent), hs*R mod n^2
+  // n*R mod n^2, hs*R mod n^2, n (exponent)
   Limbs R = hbn::pow2(32u * (unsigned)L);
   Limbs nR = hbn::mod(hbn::mul(pk->n, R), pk->nsq);
-  std::vector<uint32_t> blk((size_t)L + n_words + L, 0u);
-  hbn::to_words(nR, blk.data(), L);
-  hbn::to_words(pk->n, blk.data() + 2 * L, n_words);
+  pk->h_const.assign((size_t)L + n_words + L, 0u);
+  hbn::to_words(nR, pk->h_const.data(), L);
+  hbn::to_words(pk->n, pk->h_const.data() + 2 * L, n_words);
   if (hs) {
     pk->djn = true;
     pk->rand_bits = rand_bits > 0 ? rand_bits : n_words * 16;
     pk->hs = hbn::mod(hbn::from_words(hs, 2 * n_words), pk->nsq);
     Limbs hsm = hbn::mod(hbn::mul(pk->hs, R), pk->nsq);
-    hbn::to_words(hsm, blk.data() + L, L);
-  }
-  CUDA_TRY(cudaMalloc(&pk->d_const, blk.size() * sizeof(uint32_t)));
-  CUDA_TRY(cudaMemcpy(pk->d_const, blk.data(), blk.size() * sizeof(uint32_t),
-                      cudaMemcpyHostToDevice));
-  if (!hs) {
+    hbn::to_words(hsm, pk->h_const.data() + L, L);
+  } else {
     // non-DJN obfuscator r^n: every element has the exponent n
-    std::vector<uint8_t> sn = build_schedule(pk->n, kSchedWindow);
-    CUDA_TRY(cudaMalloc(&pk->d_sched_n, sn.size()));
-    CUDA_TRY(cudaMemcpy(pk->d_sched_n, sn.data(), sn.size(), cudaMemcpyHostToDevice));
+    pk->h_sched_n = build_schedule(pk->n, kSchedWindow);
   }
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  PubDev* pd = nullptr;
+  TRY(pub_dev(pk.get(), dev, &pd));
   *out = pk.release();
   return 0;
 }
 
 void ipclb200_pubkey_destroy(ipclb200_pubkey* pk) {
   if (!pk) return;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.ready) {
-    cudaSetDevice(g_ctx.device);
-    cudaDeviceSynchronize();
-  }
+  DeviceGuard guard;
   delete pk;
 }
 
-int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt,
-                     int pt_words, const uint32_t* r, int r_words, size_t count,
-                     int make_secure, uint32_t* ct) {
+int ipclb200_pubkey_set_table_policy(ipclb200_pubkey* pk, long max_table_mb,
+                                     long upgrade_after) {
+  if (!pk) return fail(IPCLB200_ERR_BAD_ARG, "set_table_policy: null key");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  if (max_table_mb >= 0) pk->comb_max_mb = (size_t)max_table_mb;
+  if (upgrade_after >= 0) pk->comb_upgrade_at = (size_t)upgrade_after;
+  return 0;
+}
+
+int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt, int pt_words,
+                     const uint32_t* r, int r_words, size_t count, int make_secure,
+                     uint32_t* ct) {
   if (!pk || !pt || !ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt: null pointer");
   if (make_secure && !r) return fail(IPCLB200_ERR_BAD_ARG, "encrypt: randoms missing");
   if (pt_words <= 0 || pt_words > pk->nl)
@@ -1540,33 +1594,37 @@ int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt,
   if (make_secure && (r_words <= 0 || r_words > 2 * pk->nl))
     return fail(IPCLB200_ERR_BAD_ARG, "encrypt: r_words out of range");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
+  DeviceGuard guard;
   const int L = pk->L, CW = 2 * pk->nl;
-  uint32_t *d_pt, *d_r = nullptr, *d_ct;
-  TRY(scratch_get(0, count * (size_t)pt_words, &d_pt));
-  TRY(scratch_get(2, count * (size_t)L, &d_ct));
-  CUDA_TRY(cudaMemcpyAsync(d_pt, pt, count * (size_t)pt_words * 4,
-                           cudaMemcpyHostToDevice, s));
-  int r_bits = 0;
-  if (make_secure) {
-    TRY(scratch_get(1, count * (size_t)r_words, &d_r));
-    CUDA_TRY(cudaMemcpyAsync(d_r, r, count * (size_t)r_words * 4,
-                             cudaMemcpyHostToDevice, s));
-    r_bits = max_bits(r, r_words, count, r_words);
+  const int r_bits = make_secure ? max_bits(r, r_words, count, r_words) : 0;
+  std::vector<Shard> shards;
+  TRY(plan_shards(count, &shards));
+  std::vector<Op> ops(shards.size());
+  for (size_t i = 0; i < shards.size(); i++) {
+    const Shard& sh = shards[i];
+    Op& op = ops[i];
+    TRY(op.open(sh.dev));
+    uint32_t *d_pt, *d_r = nullptr, *d_ct;
+    TRY(op.words(sh.count * (size_t)pt_words, &d_pt));
+    TRY(op.words(sh.count * (size_t)L, &d_ct));
+    CUDA_TRY(cudaMemcpyAsync(d_pt, pt + sh.begin * (size_t)pt_words,
+                             sh.count * (size_t)pt_words * 4, cudaMemcpyHostToDevice, op.s));
+    if (make_secure) {
+      TRY(op.words(sh.count * (size_t)r_words, &d_r));
+      CUDA_TRY(cudaMemcpyAsync(d_r, r + sh.begin * (size_t)r_words,
+                               sh.count * (size_t)r_words * 4, cudaMemcpyHostToDevice, op.s));
+    }
+    TRY(encrypt_dev_impl(op, pk, d_pt, pt_words, d_r, r_words, r_bits, sh.count, make_secure,
+                         d_ct));
+    TRY(download_padded(ct + sh.begin * (size_t)CW, d_ct, CW, L, sh.count, op.s));
   }
-  TRY(encrypt_dev_impl(pk, d_pt, pt_words, d_r, r_words, r_bits, count,
-                       make_secure, d_ct, s));
-  TRY(download_padded(ct, d_ct, CW, L, count, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  for (auto& op : ops) TRY(op.sync());
   return 0;
 }
 
-int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt,
-                         int pt_words, const uint32_t* d_r, int r_words,
-                         size_t count, int make_secure, uint32_t* d_ct,
-                         void* stream) {
+int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt, int pt_words,
+                         const uint32_t* d_r, int r_words, size_t count, int make_secure,
+                         uint32_t* d_ct, void* stream) {
   if (!pk || !d_pt || !d_ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: null pointer");
   if (make_secure && !d_r) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: randoms missing");
   if (pk->L != 2 * pk->nl)
@@ -1577,21 +1635,23 @@ int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt,
   if (make_secure && (r_words <= 0 || r_words > 2 * pk->nl))
     return fail(IPCLB200_ERR_BAD_ARG, "encrypt_dev: r_words out of range");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  return encrypt_dev_impl(pk, d_pt, pt_words, d_r, r_words, r_words * 32, count,
-                          make_secure, d_ct, (cudaStream_t)stream);
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_ct, &dev));
+  Op op;
+  TRY(op.open_on(dev, (cudaStream_t)stream));
+  return encrypt_dev_impl(op, pk, d_pt, pt_words, d_r, r_words, r_words * 32, count,
+                          make_secure, d_ct);
 }
 
-// ---- private key ----------------------------------------------------------
-int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
-                            int p_words, ipclb200_privkey** out) {
+// ---- private key ------------------------------------------------------------
+int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in, int p_words,
+                            ipclb200_privkey** out) {
   if (!p_in || !q_in || !out || p_words <= 0)
     return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: bad argument");
   if (2 * p_words > kMaxPrimeWords)
     return fail(IPCLB200_ERR_UNSUPPORTED, "privkey_create: primes wider than 2048 bits");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
+  if (device_count_raw() == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  DeviceGuard guard;
   std::unique_ptr<ipclb200_privkey> sk(new ipclb200_privkey);
   const int pl = p_words;
   sk->pl = pl;
@@ -1599,27 +1659,26 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   if (hbn::cmp(q, p) < 0) p.swap(q);  // pri_key.cpp:19-22
   if (p.empty() || !(p[0] & 1u) || !(q[0] & 1u))
     return fail(IPCLB200_ERR_EVEN_MODULUS, "privkey_create: p and q must be odd");
-  if (hbn::cmp(p, q) == 0)
-    return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: p and q are same");
+  if (hbn::cmp(p, q) == 0) return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: p and q are same");
   sk->p = p;
   sk->q = q;
   sk->n = hbn::mul(p, q);
   sk->nsq = hbn::mul(sk->n, sk->n);
   Limbs one = hbn::from_u64(1);
   Limbs psq = hbn::mul(p, p), qsq = hbn::mul(q, q);
+  sk->psq = psq;
+  sk->qsq = qsq;
   Limbs pm1 = hbn::sub(p, one), qm1 = hbn::sub(q, one);
-  Limbs g = hbn::add(sk->n, one);
+  Limbs gg = hbn::add(sk->n, one);
   sk->L = class_words(2 * pl);
-  TRY(make_modulus(psq, sk->L, &sk->mp2));
-  TRY(make_modulus(qsq, sk->L, &sk->mq2));
-  TRY(make_modulus(sk->nsq, class_words(4 * pl), &sk->mnsq));
+  sk->Lnsq = class_words(4 * pl);
   // computeHfun (pri_key.cpp:159-167)
   Limbs hp, hq, pinv, tmp, lq;
-  TRY(modexp_scalar(hbn::mod(g, psq), pm1, psq, &tmp));
+  TRY(modexp_scalar(hbn::mod(gg, psq), pm1, psq, &tmp));
   hbn::divmod(hbn::sub(tmp, one), p, &lq, nullptr);
   if (!hbn::modinv(lq, p, &hp))
     return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: hp not invertible (p not prime?)");
-  TRY(modexp_scalar(hbn::mod(g, qsq), qm1, qsq, &tmp));
+  TRY(modexp_scalar(hbn::mod(gg, qsq), qm1, qsq, &tmp));
   hbn::divmod(hbn::sub(tmp, one), q, &lq, nullptr);
   if (!hbn::modinv(lq, q, &hq))
     return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: hq not invertible (q not prime?)");
@@ -1630,7 +1689,7 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   hbn::divmod(hbn::mul(pm1, qm1), gc, &lam, nullptr);
   sk->lambda = lam;
   Limbs mu;
-  TRY(modexp_scalar(g, lam, sk->nsq, &tmp));
+  TRY(modexp_scalar(gg, lam, sk->nsq, &tmp));
   hbn::divmod(hbn::sub(tmp, one), sk->n, &lq, nullptr);
   if (!hbn::modinv(lq, sk->n, &mu))
     return fail(IPCLB200_ERR_BAD_ARG, "privkey_create: mu not invertible");
@@ -1642,8 +1701,8 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   Limbs muR = hbn::mod(hbn::mul(mu, Rn), sk->n);
   // device block: p q pm1 qm1 hpR hqR pinvR (pl each) | n muR (2pl each) |
   // n0inv(n^2) (1, padded to 4) | lambda (2pl)
-  std::vector<uint32_t> blk(7 * (size_t)pl + 4 * (size_t)pl + 4 + 2 * (size_t)pl, 0u);
-  uint32_t* b = blk.data();
+  sk->h_const.assign(7 * (size_t)pl + 4 * (size_t)pl + 4 + 2 * (size_t)pl, 0u);
+  uint32_t* b = sk->h_const.data();
   hbn::to_words(p, b, pl);
   hbn::to_words(q, b + pl, pl);
   hbn::to_words(pm1, b + 2 * pl, pl);
@@ -1653,22 +1712,8 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   hbn::to_words(pinvR, b + 6 * pl, pl);
   hbn::to_words(sk->n, b + 7 * pl, 2 * pl);
   hbn::to_words(muR, b + 9 * pl, 2 * pl);
-  b[11 * pl] = sk->mnsq->mc.n0inv;
+  b[11 * pl] = hbn::neg_inv32(sk->nsq[0]);
   hbn::to_words(lam, b + 11 * pl + 4, 2 * pl);
-  CUDA_TRY(cudaMalloc(&sk->d_const, blk.size() * sizeof(uint32_t)));
-  CUDA_TRY(cudaMemcpy(sk->d_const, blk.data(), blk.size() * sizeof(uint32_t),
-                      cudaMemcpyHostToDevice));
-  const uint32_t* d = sk->d_const;
-  sk->d_p = d;
-  sk->d_q = d + pl;
-  sk->d_pm1 = d + 2 * pl;
-  sk->d_qm1 = d + 3 * pl;
-  sk->d_hpR = d + 4 * pl;
-  sk->d_hqR = d + 5 * pl;
-  sk->d_pinvR = d + 6 * pl;
-  sk->d_n = d + 7 * pl;
-  sk->d_muR = d + 9 * pl;
-  sk->d_lambda = d + 11 * pl + 4;
   sk->p_n0inv = hbn::neg_inv32(p[0]);
   sk->q_n0inv = hbn::neg_inv32(q[0]);
   sk->n_n0inv = hbn::neg_inv32(sk->n[0]);
@@ -1677,28 +1722,15 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
   sk->n_inv32 = 0u - sk->n_n0inv;
   sk->pm1_bits = hbn::bitlen(pm1);
   sk->qm1_bits = hbn::bitlen(qm1);
+  sk->lambda_bits = hbn::bitlen(lam);
   {
     std::vector<uint8_t> sp = build_schedule(pm1, kSchedWindow);
     std::vector<uint8_t> sq = build_schedule(qm1, kSchedWindow);
-#ifdef IPCLB200_EXPERIMENTS
-    std::vector<uint8_t> pp = build_tile_program(sp), pq = build_tile_program(sq);
-#else
-    std::vector<uint8_t> pp, pq;
-#endif
     std::vector<uint8_t> sl = build_schedule(lam, kSchedWindow);
-    std::vector<uint8_t> both(sp);
-    both.insert(both.end(), sq.begin(), sq.end());
-    both.insert(both.end(), pp.begin(), pp.end());
-    both.insert(both.end(), pq.begin(), pq.end());
-    both.insert(both.end(), sl.begin(), sl.end());
-    CUDA_TRY(cudaMalloc(&sk->d_sched, both.size()));
-    CUDA_TRY(cudaMemcpy(sk->d_sched, both.data(), both.size(), cudaMemcpyHostToDevice));
-    sk->d_sched_p = sk->d_sched;
-    sk->d_sched_q = sk->d_sched + sp.size();
-    sk->d_sched_lambda = sk->d_sched_q + sq.size() + pp.size() + pq.size();
+    std::vector<uint8_t> pp, pq;
 #ifdef IPCLB200_EXPERIMENTS
-    sk->d_prog_p = sk->d_sched_q + sq.size();
-    sk->d_prog_q = sk->d_prog_p + pp.size();
+    pp = build_tile_program(sp);
+    pq = build_tile_program(sq);
     sk->tile_slots = sp[0] + 1;
     Limbs two256 = hbn::pow2(256), inv;
     hbn::modinv(hbn::mod(psq, two256), two256, &inv);
@@ -1706,203 +1738,503 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in,
     hbn::modinv(hbn::mod(qsq, two256), two256, &inv);
     hbn::to_words(hbn::sub(two256, inv), sk->ninv_q, 8);
 #endif
+    sk->h_sched = sp;
+    sk->off_sched_q = sk->h_sched.size();
+    sk->h_sched.insert(sk->h_sched.end(), sq.begin(), sq.end());
+    sk->off_prog_p = sk->h_sched.size();
+    sk->h_sched.insert(sk->h_sched.end(), pp.begin(), pp.end());
+    sk->off_prog_q = sk->h_sched.size();
+    sk->h_sched.insert(sk->h_sched.end(), pq.begin(), pq.end());
+    sk->off_sched_lambda = sk->h_sched.size();
+    sk->h_sched.insert(sk->h_sched.end(), sl.begin(), sl.end());
     // two-digit decrypt: needs primes that fill their words (so that a digit
     // < R is < 2p) and a prime width decrypt_hensel_kernel is instantiated for
     sk->hensel_ok = hbn::bitlen(p) == 32 * pl && hbn::bitlen(q) == 32 * pl &&
                     (pl == 16 || pl == 32 || pl == 48 || pl == 64);
     if (sk->hensel_ok) {
       std::vector<uint32_t> hs_p = hensel_schedule(sp), hs_q = hensel_schedule(sq);
-      std::vector<uint32_t> blk(20 * (size_t)pl + hs_p.size() + hs_q.size(), 0u);
-      hensel_side_block(p, psq, hp, pl, blk.data());
-      hensel_side_block(q, qsq, hq, pl, blk.data() + 10 * (size_t)pl);
-      std::copy(hs_p.begin(), hs_p.end(), blk.begin() + 20 * (size_t)pl);
-      std::copy(hs_q.begin(), hs_q.end(), blk.begin() + 20 * (size_t)pl + hs_p.size());
-      CUDA_TRY(cudaMalloc(&sk->d_hensel, blk.size() * sizeof(uint32_t)));
-      CUDA_TRY(cudaMemcpy(sk->d_hensel, blk.data(), blk.size() * sizeof(uint32_t),
-                          cudaMemcpyHostToDevice));
-      sk->d_hblk_p = sk->d_hensel;
-      sk->d_hblk_q = sk->d_hensel + 10 * (size_t)pl;
-      sk->d_hsched_p = sk->d_hensel + 20 * (size_t)pl;
-      sk->d_hsched_q = sk->d_hsched_p + hs_p.size();
+      sk->h_hensel.assign(20 * (size_t)pl + hs_p.size() + hs_q.size(), 0u);
+      hensel_side_block(p, psq, hp, pl, sk->h_hensel.data());
+      hensel_side_block(q, qsq, hq, pl, sk->h_hensel.data() + 10 * (size_t)pl);
+      sk->off_hsched_p = 20 * (size_t)pl;
+      sk->off_hsched_q = sk->off_hsched_p + hs_p.size();
+      std::copy(hs_p.begin(), hs_p.end(), sk->h_hensel.begin() + sk->off_hsched_p);
+      std::copy(hs_q.begin(), hs_q.end(), sk->h_hensel.begin() + sk->off_hsched_q);
     }
   }
-  sk->lambda_bits = hbn::bitlen(lam);
 #ifdef IPCLB200_EXPERIMENTS
-  if (sk->L == kFpWords) {
-    // radix-2^22 constants of the FP64 role: n and R^3 mod n, R = 2^(22*96)
-    constexpr int FL = kFpLimbs;
-    std::vector<double> blk(4 * (size_t)FL);
-    Limbs Rf = hbn::pow2((unsigned)(kFpW * FL));
-    const Limbs* mods[2] = {&psq, &qsq};
-    for (int i = 0; i < 2; i++) {
-      const Limbs& m = *mods[i];
-      Limbs r1 = hbn::mod(Rf, m);
-      Limbs r3 = hbn::mod(hbn::mul(hbn::mod(hbn::mul(r1, r1), m), r1), m);
-      fp_limbs(m, blk.data() + (size_t)(2 * i) * FL, FL);
-      fp_limbs(r3, blk.data() + (size_t)(2 * i + 1) * FL, FL);
-    }
-    CUDA_TRY(cudaMalloc(&sk->d_fp, blk.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(sk->d_fp, blk.data(), blk.size() * sizeof(double),
-                        cudaMemcpyHostToDevice));
-    sk->fp0.n = sk->d_fp;
-    sk->fp0.r3 = sk->d_fp + FL;
-    sk->fp0.n32 = sk->mp2->mc.n;
-    sk->fp0.n0inv = hbn::neg_inv32(psq[0]) & kFpMask;
-    sk->fp1.n = sk->d_fp + 2 * FL;
-    sk->fp1.r3 = sk->d_fp + 3 * FL;
-    sk->fp1.n32 = sk->mq2->mc.n;
-    sk->fp1.n0inv = hbn::neg_inv32(qsq[0]) & kFpMask;
-    sk->fp_ok = true;
-  }
+  privkey_experiment_constants(sk.get(), psq, qsq);
 #endif
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  PrivDev* sd = nullptr;
+  TRY(priv_dev(sk.get(), dev, &sd));
   *out = sk.release();
   return 0;
 }
 
 void ipclb200_privkey_destroy(ipclb200_privkey* sk) {
   if (!sk) return;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.ready) {
-    cudaSetDevice(g_ctx.device);
-    cudaDeviceSynchronize();
-  }
+  DeviceGuard guard;
   delete sk;
 }
 
-int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct,
-                     size_t count, int use_crt, uint32_t* pt) {
+int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct, size_t count,
+                     int use_crt, uint32_t* pt) {
   if (!sk || !ct || !pt) return fail(IPCLB200_ERR_BAD_ARG, "decrypt: null pointer");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
+  DeviceGuard guard;
   const int pl = sk->pl;
   const int CW = 4 * pl;  // caller's ciphertext words
-  uint32_t *d_ct, *d_x, *d_pt;
-  // the kernels read a ciphertext as 2L (CRT, L = class of p^2) or L (RAW,
-  // L = class of n^2) words; zero padding keeps the value
-  const int ctw = use_crt ? 2 * sk->L : sk->mnsq->L;
-  const int xw = use_crt ? 2 * sk->L : sk->mnsq->L;
-  TRY(scratch_get(0, count * (size_t)ctw, &d_ct));
-  TRY(scratch_get(1, count * (size_t)xw, &d_x));
-  TRY(scratch_get(2, count * (size_t)(2 * pl), &d_pt));
-  TRY(upload_padded(d_ct, ct, CW, ctw, count, s));
-  TRY(decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, s));
-  CUDA_TRY(cudaMemcpyAsync(pt, d_pt, count * (size_t)(2 * pl) * 4,
-                           cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  // the kernels read a ciphertext as 2L (CRT, L = class of p^2) or Lnsq (RAW)
+  // words; zero padding keeps the value
+  const int ctw = use_crt ? 2 * sk->L : sk->Lnsq;
+  std::vector<Shard> shards;
+  TRY(plan_shards(count, &shards));
+  std::vector<Op> ops(shards.size());
+  for (size_t i = 0; i < shards.size(); i++) {
+    const Shard& sh = shards[i];
+    Op& op = ops[i];
+    TRY(op.open(sh.dev));
+    uint32_t *d_ct, *d_pt;
+    TRY(op.words(sh.count * (size_t)ctw, &d_ct));
+    TRY(op.words(sh.count * (size_t)(2 * pl), &d_pt));
+    TRY(upload_padded(d_ct, ct + sh.begin * (size_t)CW, CW, ctw, sh.count, op.s));
+    TRY(decrypt_dev_impl(op, sk, d_ct, sh.count, use_crt, d_pt));
+    CUDA_TRY(cudaMemcpyAsync(pt + sh.begin * (size_t)(2 * pl), d_pt,
+                             sh.count * (size_t)(2 * pl) * 4, cudaMemcpyDeviceToHost, op.s));
+  }
+  for (auto& op : ops) TRY(op.sync());
   return 0;
 }
 
-int ipclb200_crt_residues(const ipclb200_privkey* sk, const uint32_t* ct,
-                          size_t count, uint32_t* x, int* x_words) {
+int ipclb200_crt_residues(const ipclb200_privkey* sk, const uint32_t* ct, size_t count,
+                          uint32_t* x, int* x_words) {
   if (!sk || !ct || !x) return fail(IPCLB200_ERR_BAD_ARG, "crt_residues: null pointer");
   if (x_words) *x_words = sk->L;
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
+  DeviceGuard guard;
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  PrivDev* sd = nullptr;
+  TRY(priv_dev(sk, dev, &sd));
+  Op op;
+  TRY(op.open(dev));
   const int pl = sk->pl;
-  uint32_t *d_ct, *d_x, *d_pt;
-  TRY(scratch_get(0, count * (size_t)(2 * sk->L), &d_ct));
-  TRY(scratch_get(1, count * (size_t)(2 * sk->L), &d_x));
-  TRY(scratch_get(2, count * (size_t)(2 * pl), &d_pt));
-  TRY(upload_padded(d_ct, ct, 4 * pl, 2 * sk->L, count, s));
-  TRY(decrypt_dev_impl(sk, d_ct, count, 1, d_pt, d_x, s));
-  CUDA_TRY(cudaMemcpyAsync(x, d_x, count * (size_t)(2 * sk->L) * 4,
-                           cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  return 0;
+  uint32_t *d_ct, *d_x;
+  TRY(op.words(count * (size_t)(2 * sk->L), &d_ct));
+  TRY(op.words(count * (size_t)(2 * sk->L), &d_x));
+  TRY(upload_padded(d_ct, ct, 4 * pl, 2 * sk->L, count, op.s));
+  TRY(crt_residues_impl(op, sk, sd, d_ct, count, d_x));
+  CUDA_TRY(cudaMemcpyAsync(x, d_x, count * (size_t)(2 * sk->L) * 4, cudaMemcpyDeviceToHost,
+                           op.s));
+  return op.sync();
 }
 
-int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct,
-                         size_t count, int use_crt, uint32_t* d_pt,
-                         void* stream) {
+int ipclb200_decrypt_dev(const ipclb200_privkey* sk, const uint32_t* d_ct, size_t count,
+                         int use_crt, uint32_t* d_pt, void* stream) {
   if (!sk || !d_ct || !d_pt) return fail(IPCLB200_ERR_BAD_ARG, "decrypt_dev: null pointer");
   if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
   const int pl = sk->pl;
-  if ((use_crt && sk->L != 2 * pl) || (!use_crt && sk->mnsq->L != 4 * pl))
+  if ((use_crt && sk->L != 2 * pl) || (!use_crt && sk->Lnsq != 4 * pl))
     return fail(IPCLB200_ERR_UNSUPPORTED, "decrypt_dev: key width is not a kernel size class");
-  uint32_t* d_x;
-  TRY(scratch_get(6, count * (size_t)(4 * pl), &d_x));
-  return decrypt_dev_impl(sk, d_ct, count, use_crt, d_pt, d_x, (cudaStream_t)stream);
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_pt, &dev));
+  Op op;
+  TRY(op.open_on(dev, (cudaStream_t)stream));
+  // every intermediate of this call is allocated on the caller's stream: calls
+  // on different streams share nothing
+  return decrypt_dev_impl(op, sk, d_ct, count, use_crt, d_pt);
 }
 
-// ---- device-resident batches ------------------------------------------------
+// ---- device-resident buffers on the primary device ----------------------------
 void* ipclb200_stream(void) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (ensure_init_locked() != 0) return nullptr;
-  return (void*)g_ctx.stream;
+  Dev* d = nullptr;
+  if (primary_device(&d) != 0) return nullptr;
+  return (void*)d->stream;
 }
 
 int ipclb200_dev_alloc(size_t bytes, void** d_out) {
   if (!d_out) return fail(IPCLB200_ERR_BAD_ARG, "dev_alloc: null pointer");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  CUDA_TRY(cudaMallocAsync(d_out, bytes ? bytes : 4, g_ctx.stream));
+  Dev* d = nullptr;
+  TRY(primary_device(&d));
+  CUDA_TRY(cudaSetDevice(d->id));
+  CUDA_TRY(cudaMallocAsync(d_out, bytes ? bytes : 4, d->stream));
   return 0;
 }
 
-int ipclb200_dev_free(void* d) {
+int ipclb200_dev_free(void* p) {
+  if (!p) return 0;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // the context (and its pool) is already gone
+  }
+  Dev* d = at.device >= 0 && at.device < kMaxDevices ? g.dev[at.device].load() : nullptr;
   if (!d) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (!g_ctx.ready) return 0;  // the context (and its pool) is already gone
-  CUDA_TRY(cudaSetDevice(g_ctx.device));
-  CUDA_TRY(cudaFreeAsync(d, g_ctx.stream));
+  CUDA_TRY(cudaSetDevice(d->id));
+  CUDA_TRY(cudaFreeAsync(p, d->stream));
   return 0;
 }
 
 int ipclb200_dev_upload(void* d, const void* h, size_t bytes) {
   if (!d || !h) return fail(IPCLB200_ERR_BAD_ARG, "dev_upload: null pointer");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d, &dev));
+  CUDA_TRY(cudaSetDevice(dev->id));
   // pageable source: the call returns once the data is staged, so the caller
   // may reuse h; pinned source: wait for the copy
-  CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
   cudaPointerAttributes at{};
-  if (cudaPointerGetAttributes(&at, h) == cudaSuccess &&
-      at.type == cudaMemoryTypeHost)
-    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost)
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
   cudaGetLastError();
   return 0;
 }
 
 int ipclb200_dev_download(void* h, const void* d, size_t bytes) {
   if (!d || !h) return fail(IPCLB200_ERR_BAD_ARG, "dev_download: null pointer");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
-  CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d, &dev));
+  CUDA_TRY(cudaSetDevice(dev->id));
+  CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  CUDA_TRY(cudaStreamSynchronize(dev->stream));
   return 0;
 }
 
 int ipclb200_dev_copy(void* d_dst, const void* d_src, size_t bytes) {
   if (!d_dst || !d_src) return fail(IPCLB200_ERR_BAD_ARG, "dev_copy: null pointer");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_dst, &dev));
+  CUDA_TRY(cudaSetDevice(dev->id));
+  CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, dev->stream));
   return 0;
 }
 
 int ipclb200_sync(void) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+  if (device_count_raw() == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  DeviceGuard guard;
+  for (auto& slot : g.dev) {
+    Dev* d = slot.load();
+    if (!d) continue;
+    CUDA_TRY(cudaSetDevice(d->id));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+  }
   return 0;
 }
 
 int ipclb200_class_words(int words) { return words > 0 ? class_words(words) : 0; }
 
+// page-locked host memory for callers that are not CUDA programs themselves
+// (the ipcl:: layer stages vector<BigNumber> batches through it)
+int ipclb200_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(IPCLB200_ERR_BAD_ARG, "host_alloc: null pointer");
+  if (device_count_raw() == 0) return fail(IPCLB200_ERR_NO_DEVICE, "no CUDA device");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocPortable));
+  return 0;
+}
+
+int ipclb200_host_free(void* p) {
+  if (!p) return 0;
+  cudaFreeHost(p);
+  cudaGetLastError();
+  return 0;
+}
+
+// ---- batches sharded over the active devices -------------------------------------
+int ipclb200_batch_alloc(size_t count, int words, ipclb200_batch** out) {
+  if (!out || words <= 0) return fail(IPCLB200_ERR_BAD_ARG, "batch_alloc: bad argument");
+  DeviceGuard guard;
+  std::unique_ptr<ipclb200_batch> b(new ipclb200_batch);
+  b->count = count;
+  b->words = words;
+  TRY(plan_shards(count, &b->shards));
+  for (auto& sh : b->shards) {
+    uint32_t* p = nullptr;
+    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(16, sh.count * (size_t)words * 4),
+                             sh.dev->stream));
+    b->d.push_back(p);
+  }
+  *out = b.release();
+  return 0;
+}
+
+void ipclb200_batch_free(ipclb200_batch* b) {
+  if (!b) return;
+  DeviceGuard guard;
+  for (size_t i = 0; i < b->d.size(); i++) {
+    Dev* d = b->shards[i].dev;
+    bool alive = false;
+    for (auto& slot : g.dev)
+      if (slot.load() == d) alive = true;
+    if (!alive) continue;  // after shutdown: the pool is gone
+    cudaSetDevice(d->id);
+    cudaFreeAsync(b->d[i], d->stream);
+  }
+  delete b;
+}
+
+size_t ipclb200_batch_count(const ipclb200_batch* b) { return b ? b->count : 0; }
+int ipclb200_batch_words(const ipclb200_batch* b) { return b ? b->words : 0; }
+int ipclb200_batch_num_shards(const ipclb200_batch* b) { return b ? (int)b->shards.size() : 0; }
+
+int ipclb200_batch_shard(const ipclb200_batch* b, int shard, int* device, void** d_ptr,
+                         size_t* begin, size_t* count, void** stream) {
+  if (!b || shard < 0 || shard >= (int)b->shards.size())
+    return fail(IPCLB200_ERR_BAD_ARG, "batch_shard: bad argument");
+  if (device) *device = b->shards[shard].dev->id;
+  if (d_ptr) *d_ptr = b->d[shard];
+  if (begin) *begin = b->shards[shard].begin;
+  if (count) *count = b->shards[shard].count;
+  if (stream) *stream = (void*)b->shards[shard].dev->stream;
+  return 0;
+}
+
+// host (count x h_words, h_words <= words) -> shards, zero padded
+int ipclb200_batch_upload(ipclb200_batch* b, const uint32_t* h, int h_words) {
+  if (!b || !h || h_words <= 0 || h_words > b->words)
+    return fail(IPCLB200_ERR_BAD_ARG, "batch_upload: bad argument");
+  DeviceGuard guard;
+  bool pinned = false;
+  {
+    cudaPointerAttributes at{};
+    pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+  }
+  for (size_t i = 0; i < b->shards.size(); i++) {
+    const Shard& sh = b->shards[i];
+    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    TRY(upload_padded(b->d[i], h + sh.begin * (size_t)h_words, h_words, b->words, sh.count,
+                      sh.dev->stream));
+  }
+  if (pinned)
+    for (auto& sh : b->shards) {
+      CUDA_TRY(cudaSetDevice(sh.dev->id));
+      CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+    }
+  return 0;
+}
+
+int ipclb200_batch_download(const ipclb200_batch* b, uint32_t* h, int h_words) {
+  if (!b || !h || h_words <= 0 || h_words > b->words)
+    return fail(IPCLB200_ERR_BAD_ARG, "batch_download: bad argument");
+  DeviceGuard guard;
+  for (size_t i = 0; i < b->shards.size(); i++) {
+    const Shard& sh = b->shards[i];
+    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    TRY(download_padded(h + sh.begin * (size_t)h_words, b->d[i], h_words, b->words, sh.count,
+                        sh.dev->stream));
+  }
+  for (auto& sh : b->shards) {
+    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+  }
+  return 0;
+}
+
+int ipclb200_batch_sync(const ipclb200_batch* b) {
+  if (!b) return 0;
+  DeviceGuard guard;
+  for (auto& sh : b->shards) {
+    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+  }
+  return 0;
+}
+
+// scatter: a contiguous device buffer (count x words, on the device of shard 0)
+// -> the shards; gather: the reverse.  NCCL grouped send/recv over NVLink
+// (NCCL has no native scatter/gather); one device: a copy.
+static int batch_exchange(ipclb200_batch* b, uint32_t* d_flat, bool scatter) {
+  if (!b || !d_flat) return fail(IPCLB200_ERR_BAD_ARG, "batch scatter/gather: null pointer");
+  DeviceGuard guard;
+  const size_t W = (size_t)b->words;
+  Dev* root = b->shards[0].dev;
+  {
+    Dev* owner = nullptr;
+    TRY(dev_of_pointer(d_flat, &owner));
+    if (owner != root)
+      return fail(IPCLB200_ERR_BAD_ARG,
+                  "batch scatter/gather: buffer is not on the first device");
+  }
+  CUDA_TRY(cudaSetDevice(root->id));
+  if (scatter)
+    CUDA_TRY(cudaMemcpyAsync(b->d[0], d_flat, b->shards[0].count * W * 4,
+                             cudaMemcpyDeviceToDevice, root->stream));
+  else
+    CUDA_TRY(cudaMemcpyAsync(d_flat, b->d[0], b->shards[0].count * W * 4,
+                             cudaMemcpyDeviceToDevice, root->stream));
+  if (b->shards.size() == 1) return 0;
+  std::lock_guard<std::mutex> lk(g_nccl.mu);
+  TRY(nccl_comms(b->shards));
+  NCCL_TRY(g_nccl.GroupStart());
+  for (size_t i = 1; i < b->shards.size(); i++) {
+    const Shard& sh = b->shards[i];
+    uint32_t* at_root = d_flat + sh.begin * W;
+    if (scatter) {
+      NCCL_TRY(g_nccl.Send(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
+                           root->stream));
+      NCCL_TRY(g_nccl.Recv(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i],
+                           sh.dev->stream));
+    } else {
+      NCCL_TRY(g_nccl.Send(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i],
+                           sh.dev->stream));
+      NCCL_TRY(g_nccl.Recv(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
+                           root->stream));
+    }
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return 0;
+}
+
+int ipclb200_batch_scatter(ipclb200_batch* b, const uint32_t* d_src) {
+  return batch_exchange(b, const_cast<uint32_t*>(d_src), true);
+}
+int ipclb200_batch_gather(const ipclb200_batch* b, uint32_t* d_dst) {
+  return batch_exchange(const_cast<ipclb200_batch*>(b), d_dst, false);
+}
+
+int ipclb200_encrypt_batch(const ipclb200_pubkey* pk, const ipclb200_batch* pt,
+                           const ipclb200_batch* r, int r_bits, int make_secure,
+                           ipclb200_batch* ct) {
+  if (!pk || !pt || !ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_batch: null pointer");
+  if (make_secure && !r) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_batch: randoms missing");
+  if (pk->L != 2 * pk->nl || ct->words != pk->L)
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "encrypt_batch: ciphertext words must be 2*n_words, a size class");
+  if (pt->words > pk->nl || (make_secure && r->words > 2 * pk->nl))
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt_batch: operand too wide");
+  if (!same_plan(pt, ct) || (make_secure && !same_plan(r, ct)))
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt_batch: batches are sharded differently");
+  DeviceGuard guard;
+  for (size_t i = 0; i < ct->shards.size(); i++) {
+    const Shard& sh = ct->shards[i];
+    if (sh.count == 0) continue;
+    Op op;
+    TRY(op.open_on(sh.dev, sh.dev->stream));
+    TRY(encrypt_dev_impl(op, pk, pt->d[i], pt->words, make_secure ? r->d[i] : nullptr,
+                         make_secure ? r->words : 0,
+                         make_secure ? (r_bits > 0 ? r_bits : r->words * 32) : 0, sh.count,
+                         make_secure, ct->d[i]));
+  }
+  return 0;
+}
+
+int ipclb200_decrypt_batch(const ipclb200_privkey* sk, const ipclb200_batch* ct, int use_crt,
+                           ipclb200_batch* pt) {
+  if (!sk || !ct || !pt) return fail(IPCLB200_ERR_BAD_ARG, "decrypt_batch: null pointer");
+  const int pl = sk->pl;
+  if ((use_crt && sk->L != 2 * pl) || (!use_crt && sk->Lnsq != 4 * pl) ||
+      ct->words != 4 * pl || pt->words != 2 * pl)
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "decrypt_batch: key width is not a kernel size class");
+  if (!same_plan(ct, pt))
+    return fail(IPCLB200_ERR_BAD_ARG, "decrypt_batch: batches are sharded differently");
+  DeviceGuard guard;
+  for (size_t i = 0; i < ct->shards.size(); i++) {
+    const Shard& sh = ct->shards[i];
+    if (sh.count == 0) continue;
+    Op op;
+    TRY(op.open_on(sh.dev, sh.dev->stream));
+    TRY(decrypt_dev_impl(op, sk, ct->d[i], sh.count, use_crt, pt->d[i]));
+  }
+  return 0;
+}
+
+int ipclb200_modmul_batch(const ipclb200_batch* a, const ipclb200_batch* b,
+                          const uint32_t* h_b_shared, const uint32_t* h_mod, int mod_words,
+                          ipclb200_batch* out) {
+  if (!a || !out || !h_mod || (!b && !h_b_shared))
+    return fail(IPCLB200_ERR_BAD_ARG, "modmul_batch: null pointer");
+  if (class_words(mod_words) != mod_words || a->words != mod_words || out->words != mod_words ||
+      (b && b->words != mod_words))
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "modmul_batch: words must equal mod_words, a size class");
+  if (!same_plan(a, out) || (b && !same_plan(b, out)))
+    return fail(IPCLB200_ERR_BAD_ARG, "modmul_batch: batches are sharded differently");
+  Limbs n;
+  TRY(check_modulus(h_mod, mod_words, &n));
+  DeviceGuard guard;
+  for (size_t i = 0; i < out->shards.size(); i++) {
+    const Shard& sh = out->shards[i];
+    if (sh.count == 0) continue;
+    Op op;
+    TRY(op.open_on(sh.dev, sh.dev->stream));
+    const uint32_t* d_b = b ? b->d[i] : nullptr;
+    if (!b) {
+      uint32_t* t;
+      TRY(op.words(mod_words, &t));
+      CUDA_TRY(cudaMemcpyAsync(t, h_b_shared, (size_t)mod_words * 4, cudaMemcpyHostToDevice,
+                               op.s));
+      d_b = t;
+    }
+    TRY(modmul_on(op, a->d[i], d_b, n, mod_words, sh.count, b ? 0u : IPCLB200_SHARED_B,
+                  out->d[i]));
+  }
+  return 0;
+}
+
+int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
+                          const uint32_t* h_exp_shared, int exp_words, int exp_bits,
+                          const uint32_t* h_mod, int mod_words, ipclb200_batch* out) {
+  if (!base || !out || !h_mod || (!exp && !h_exp_shared) || exp_words <= 0)
+    return fail(IPCLB200_ERR_BAD_ARG, "modexp_batch: bad argument");
+  if (class_words(mod_words) != mod_words || base->words != mod_words ||
+      out->words != mod_words || (exp && exp->words != exp_words))
+    return fail(IPCLB200_ERR_UNSUPPORTED,
+                "modexp_batch: words must equal mod_words, a size class");
+  if (!same_plan(base, out) || (exp && !same_plan(exp, out)))
+    return fail(IPCLB200_ERR_BAD_ARG, "modexp_batch: batches are sharded differently");
+  Limbs n;
+  TRY(check_modulus(h_mod, mod_words, &n));
+  DeviceGuard guard;
+  std::vector<uint8_t> sched;
+  if (!exp) {
+    const int eb = max_bits(h_exp_shared, exp_words, 1, exp_words);
+    if (exp_bits <= 0) exp_bits = eb;
+    const char* ns = getenv("IPCLB200_NO_SCHED");
+    if (out->count >= 64 && eb > 64 && !(ns && ns[0] == '1'))
+      sched = build_schedule(hbn::from_words(h_exp_shared, exp_words), kSchedWindow);
+  }
+  for (size_t i = 0; i < out->shards.size(); i++) {
+    const Shard& sh = out->shards[i];
+    if (sh.count == 0) continue;
+    Op op;
+    TRY(op.open_on(sh.dev, sh.dev->stream));
+    const uint32_t* d_exp = exp ? exp->d[i] : nullptr;
+    const uint8_t* d_sched = nullptr;
+    if (!exp) {
+      uint32_t* t;
+      TRY(op.words(exp_words, &t));
+      CUDA_TRY(cudaMemcpyAsync(t, h_exp_shared, (size_t)exp_words * 4, cudaMemcpyHostToDevice,
+                               op.s));
+      d_exp = t;
+      if (!sched.empty()) {
+        uint32_t* sc;
+        TRY(op.words((sched.size() + 3) / 4, &sc));
+        CUDA_TRY(cudaMemcpyAsync(sc, sched.data(), sched.size(), cudaMemcpyHostToDevice, op.s));
+        d_sched = reinterpret_cast<const uint8_t*>(sc);
+      }
+    }
+    TRY(modexp_shared_dev(op, base->d[i], d_exp, n, mod_words, exp_words, exp_bits, sh.count,
+                          IPCLB200_SHARED_MOD | (exp ? 0u : IPCLB200_SHARED_EXP), d_sched,
+                          out->d[i]));
+    if (!exp) CUDA_TRY(cudaStreamSynchronize(op.s));  // pageable staging of sched / h_exp
+  }
+  return 0;
+}
+
 // ---- measurement ----------------------------------------------------------
 int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
-  const int threads = 256, blocks = g_ctx.sms * 8;
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  Op op;
+  TRY(op.open(dev));
+  cudaStream_t s = op.s;
+  const int threads = 256, blocks = dev->sms * 8;
   uint32_t* d_out;
-  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
+  TRY(op.words((size_t)threads * blocks, &d_out));
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));
@@ -1916,14 +2248,14 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
     CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
     if (rep > 0 && ms < best) best = ms;
   }
-  g_ctx.launches += 6;
+  g.launches += 6;
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   double macs = (double)threads * blocks * kPeakIters * 16.0;
   if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
   if (sm_clock_mhz) {
     int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_ctx.device);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev->id);
     *sm_clock_mhz = khz / 1000.0;
   }
   return 0;
@@ -1932,12 +2264,14 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
 int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s) {
   if (!mac32_per_s || seconds <= 0 || seconds > 20)
     return fail(IPCLB200_ERR_BAD_ARG, "int_peak_sustained: bad argument");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
-  const int threads = 256, blocks = g_ctx.sms * 8;
+  Dev* dev = nullptr;
+  TRY(primary_device(&dev));
+  Op op;
+  TRY(op.open(dev));
+  cudaStream_t s = op.s;
+  const int threads = 256, blocks = dev->sms * 8;
   uint32_t* d_out;
-  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
+  TRY(op.words((size_t)threads * blocks, &d_out));
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));
@@ -1959,7 +2293,7 @@ int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s) {
   CUDA_TRY(cudaEventSynchronize(b));
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
-  g_ctx.launches += launches + 1;
+  g.launches += launches + 1;
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   *mac32_per_s = (double)threads * blocks * kPeakIters * 16.0 * launches / (ms * 1e-3);
@@ -1969,84 +2303,19 @@ int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s) {
 int ipclb200_debug_montsqr(const uint32_t* a, const uint32_t* mod, size_t count,
                            uint32_t* out_sqr, uint32_t* out_mul) {
 #ifndef IPCLB200_EXPERIMENTS
+  (void)a; (void)mod; (void)count; (void)out_sqr; (void)out_mul;
   return fail(IPCLB200_ERR_UNSUPPORTED, "debug_montsqr: built without -DIPCLB200_EXPERIMENTS");
 #else
-  if (!a || !mod || !out_sqr || !out_mul)
-    return fail(IPCLB200_ERR_BAD_ARG, "debug_montsqr: null pointer");
-  if (count == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
-  const int L = 64;
-  Limbs n;
-  TRY(check_modulus(mod, L, &n));
-  std::shared_ptr<DevModulus> dm;
-  TRY(make_modulus(n, L, &dm));
-  uint32_t *d_a, *d_s, *d_m;
-  TRY(scratch_get(0, count * (size_t)L, &d_a));
-  TRY(scratch_get(1, count * (size_t)L, &d_s));
-  TRY(scratch_get(2, count * (size_t)L, &d_m));
-  CUDA_TRY(cudaMemcpyAsync(d_a, a, count * (size_t)L * 4, cudaMemcpyHostToDevice, s));
-  MontSqrTestParams p{};
-  p.a = d_a;
-  p.n = dm->mc.n;
-  p.n0inv = dm->mc.n0inv;
-  p.out_sqr = d_s;
-  p.out_mul = d_m;
-  p.count = count;
-  const char* lay = getenv("IPCLB200_DEBUG_SQR_LAYOUT");
-  if (lay && lay[0] == '2') {
-    constexpr size_t smem = sqr2_smem_bytes(kBlockThreads);
-    CUDA_TRY(cudaFuncSetAttribute(montsqr2_test_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)((count + 63) / 64);
-    montsqr2_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
-  } else {
-    constexpr size_t smem = sqr_smem_bytes(kBlockThreads, 4);
-    CUDA_TRY(cudaFuncSetAttribute(montsqr_test_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)((count + 31) / 32);
-    montsqr_test_kernel<<<grid, kBlockThreads, smem, s>>>(p);
-  }
-  g_ctx.launches++;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(out_sqr, d_s, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(out_mul, d_m, count * (size_t)L * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  return 0;
+  return debug_montsqr_experiment(a, mod, count, out_sqr, out_mul);
 #endif
 }
 
 int ipclb200_pipe_mix(int mode, double* ms_out) {
 #ifndef IPCLB200_EXPERIMENTS
+  (void)mode; (void)ms_out;
   return fail(IPCLB200_ERR_UNSUPPORTED, "pipe_mix: built without -DIPCLB200_EXPERIMENTS");
 #else
-  if (mode < 0 || mode > 8 || !ms_out)
-    return fail(IPCLB200_ERR_BAD_ARG, "pipe_mix: bad argument");
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  TRY(ensure_init_locked());
-  cudaStream_t s = g_ctx.stream;
-  const int threads = 256, blocks = g_ctx.sms * 4, iters = 4096;
-  uint32_t* d_out;
-  TRY(scratch_get(7, (size_t)threads * blocks, &d_out));
-  cudaEvent_t a, b;
-  CUDA_TRY(cudaEventCreate(&a));
-  CUDA_TRY(cudaEventCreate(&b));
-  float best = 1e30f;
-  for (int rep = 0; rep < 4; rep++) {
-    CUDA_TRY(cudaEventRecord(a, s));
-    pipe_mix_kernel<<<blocks, threads, 0, s>>>(d_out, mode, iters, 3u + rep, 1.5);
-    CUDA_TRY(cudaEventRecord(b, s));
-    CUDA_TRY(cudaEventSynchronize(b));
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
-    if (rep > 0 && ms < best) best = ms;
-  }
-  g_ctx.launches += 4;
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  *ms_out = best;
-  return 0;
+  return pipe_mix_experiment(mode, ms_out);
 #endif
 }
 

@@ -228,6 +228,7 @@ struct ModmulParams {
   ModConst m;
   uint32_t* out;
   size_t count;
+  unsigned int* work_counter;
 };
 
 template <int K, int T>
@@ -235,15 +236,15 @@ __global__ void __launch_bounds__(kBlockThreads)
     modmul_kernel(const ModmulParams p) {
   using M = Mont<K, T>;
   constexpr int L = K * T;
-  const size_t gpb = blockDim.x / T;
-  const size_t gid = blockIdx.x * gpb + threadIdx.x / T;
-  const size_t ngroups = (size_t)gridDim.x * gpb;
-  const size_t iters = (p.count + ngroups - 1) / ngroups;
+  constexpr int GW = 32 / T;
   uint32_t n[K], rr[K];
   M::load(n, p.m.n);
   M::load(rr, p.m.rr);
-  for (size_t it = 0; it < iters; it++) {
-    const size_t inst = it * ngroups + gid;
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int w = claim_chunk(p.work_counter);
+    if (w >= nchunks) break;
+    const size_t inst = (size_t)w * GW + (threadIdx.x & 31) / T;
     const bool valid = inst < p.count;
     const size_t ii = valid ? inst : p.count - 1;
     uint32_t a[K], b[K];

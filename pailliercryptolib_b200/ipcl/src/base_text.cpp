@@ -30,6 +30,43 @@ std::vector<BigNumber> rotated(const std::vector<BigNumber>& v, int shift) {
   return out;
 }
 
+PinnedBuffer& PinnedBuffer::forThread() {
+  thread_local PinnedBuffer b;
+  return b;
+}
+
+uint32_t* PinnedBuffer::get(std::size_t words) {
+  if (words > m_words) {
+    if (m_p) {
+      if (m_pinned)
+        ipclb200_host_free(m_p);
+      else
+        std::free(m_p);
+      m_p = nullptr;
+    }
+    const std::size_t want = words + words / 4 + 1024;
+    void* p = nullptr;
+    if (ipclb200_host_alloc(want * sizeof(uint32_t), &p) == 0) {
+      m_pinned = true;
+    } else {
+      p = std::malloc(want * sizeof(uint32_t));
+      ERROR_CHECK(p != nullptr, "out of host memory");
+      m_pinned = false;
+    }
+    m_p = static_cast<uint32_t*>(p);
+    m_words = want;
+  }
+  return m_p;
+}
+
+PinnedBuffer::~PinnedBuffer() {
+  if (!m_p) return;
+  if (m_pinned)
+    ipclb200_host_free(m_p);
+  else
+    std::free(m_p);
+}
+
 bool deviceResidentEnabled() {
   static const bool on = [] {
     const char* e = std::getenv("IPCL_B200_DEVICE_RESIDENT");

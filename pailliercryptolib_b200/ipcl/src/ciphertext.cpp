@@ -51,14 +51,23 @@ CipherText CipherText::operator+(const CipherText& other) const {
   const int W = 2 * static_cast<int>(m_pk->getN()->words().size());
   if (detail::deviceResidentEnabled() && detail::isClassWords(W)) {
     auto a = deviceBatch(W);
-    auto b = a ? other.deviceBatch(W) : nullptr;
+    // a size-1 right operand is sharded differently: it goes down as one
+    // shared host value instead
+    auto b = (a && b_size != 1) ? other.deviceBatch(W) : nullptr;
+    if (a && b_size == 1) {
+      std::vector<uint32_t> mod(static_cast<std::size_t>(W)), bw(static_cast<std::size_t>(W));
+      m_pk->getNSQ()->toWords(mod.data(), mod.size());
+      const BigNumber bv = other.texts().front() % *(m_pk->getNSQ());
+      bv.toWords(bw.data(), bw.size());
+      auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
+      DEVICE_CHECK(ipclb200_modmul_batch(a->h, nullptr, bw.data(), mod.data(), W, out->h));
+      return CipherText(*m_pk, std::move(out));
+    }
     if (a && b) {
       std::vector<uint32_t> mod(static_cast<std::size_t>(W));
       m_pk->getNSQ()->toWords(mod.data(), mod.size());
       auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
-      DEVICE_CHECK(ipclb200_modmul_dev(a->ptr(), b->ptr(), mod.data(), W, m_size,
-                                       b_size == 1 ? IPCLB200_SHARED_B : 0u,
-                                       out->ptr(), ipclb200_stream()));
+      DEVICE_CHECK(ipclb200_modmul_batch(a->h, b->h, nullptr, mod.data(), W, out->h));
       return CipherText(*m_pk, std::move(out));
     }
   }
@@ -91,15 +100,26 @@ CipherText CipherText::operator*(const PlainText& other) const {
       ebits = 32 * ew;
     }
     auto a = deviceBatch(W);
-    auto e = a ? other.deviceBatch(ew) : nullptr;
+    if (a && b_size == 1 && !other.texts().front().isNegative()) {
+      // one exponent for the whole batch: a shared host value (sliding-window
+      // schedule on the device)
+      std::vector<uint32_t> mod(static_cast<std::size_t>(W));
+      m_pk->getNSQ()->toWords(mod.data(), mod.size());
+      const auto& ev = other.texts().front().words();
+      std::vector<uint32_t> ex(ev.empty() ? std::vector<uint32_t>(1, 0u) : ev);
+      auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
+      DEVICE_CHECK(ipclb200_modexp_batch(a->h, nullptr, ex.data(),
+                                         static_cast<int>(ex.size()), 0, mod.data(), W,
+                                         out->h));
+      return CipherText(*m_pk, std::move(out));
+    }
+    auto e = (a && b_size != 1) ? other.deviceBatch(ew) : nullptr;
     if (a && e) {
       std::vector<uint32_t> mod(static_cast<std::size_t>(W));
       m_pk->getNSQ()->toWords(mod.data(), mod.size());
       auto out = std::make_shared<detail::DeviceBatch>(m_size, W);
-      DEVICE_CHECK(ipclb200_modexp_dev(
-          a->ptr(), e->ptr(), mod.data(), W, ew, ebits > 0 ? ebits : 1, m_size,
-          IPCLB200_SHARED_MOD | (b_size == 1 ? IPCLB200_SHARED_EXP : 0u),
-          out->ptr(), ipclb200_stream()));
+      DEVICE_CHECK(ipclb200_modexp_batch(a->h, e->h, nullptr, ew, ebits > 0 ? ebits : 1,
+                                         mod.data(), W, out->h));
       return CipherText(*m_pk, std::move(out));
     }
   }

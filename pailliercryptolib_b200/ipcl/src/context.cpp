@@ -21,7 +21,15 @@ bool initializeContext(const std::string runtime_choice) {
   ERROR_CHECK(c == "DEFAULT" || c == "CPU" || c == "QAT" || c == "HYBRID" ||
                   c == "GPU" || c == "B200",
               "initializeContext: unknown runtime choice " + runtime_choice);
-  DEVICE_CHECK(ipclb200_init(-1));
+  // IPCLB200_DEVICES=n (or "all"): one process drives n GPUs, every batch is
+  // split over them (the slot of the reference's CPU/QAT split, mod_exp.cpp:702-731)
+  const char* nd = std::getenv("IPCLB200_DEVICES");
+  if (nd && *nd) {
+    const int n = (std::string(nd) == "all") ? 0 : std::atoi(nd);
+    DEVICE_CHECK(ipclb200_init_devices(n));
+  } else {
+    DEVICE_CHECK(ipclb200_init(-1));
+  }
   g_gpu_up = true;
   return true;
 }

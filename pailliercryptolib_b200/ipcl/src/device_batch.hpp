@@ -1,10 +1,11 @@
 // device_batch.hpp -- a batch of big integers resident in HBM: count x words
-// little-endian 32-bit limbs, element-major, the layout every *_dev entry
-// point of include/ipcl_b200.h reads and writes.  Owned through shared_ptr by
-// the texts that refer to it; immutable once its producer kernel is enqueued.
-// Allocation, copies, kernels and the free are all ordered on the library
-// stream (ipclb200_stream()), so no host synchronisation is needed until a
-// caller asks for the values (toHost()).
+// little-endian 32-bit limbs, element-major, sharded in contiguous blocks over
+// the GPUs the library was initialised on (ipclb200_batch_*,
+// include/ipcl_b200.h).  Owned through shared_ptr by the texts that refer to
+// it; immutable once its producer kernel is enqueued.  Allocation, copies,
+// kernels and the free are ordered on the library stream of each shard's
+// device, so no host synchronisation is needed until a caller asks for the
+// values (toHost()).
 //
 // This is the device-resident CipherText of SURVEY.md section 8f row 2: the
 // reference copies vector<BigNumber> at every step (ipcl/base_text.cpp:102,
@@ -26,23 +27,18 @@ namespace ipcl {
 namespace detail {
 
 struct DeviceBatch {
-  void* d = nullptr;
+  ipclb200_batch* h = nullptr;
   std::size_t count = 0;
   int words = 0;
 
   DeviceBatch(std::size_t count_, int words_) : count(count_), words(words_) {
-    DEVICE_CHECK(ipclb200_dev_alloc(bytes(), &d));
+    DEVICE_CHECK(ipclb200_batch_alloc(count, words, &h));
   }
   ~DeviceBatch() {
-    if (d) ipclb200_dev_free(d);
+    if (h) ipclb200_batch_free(h);
   }
   DeviceBatch(const DeviceBatch&) = delete;
   DeviceBatch& operator=(const DeviceBatch&) = delete;
-
-  std::size_t bytes() const {
-    return count * static_cast<std::size_t>(words) * sizeof(uint32_t);
-  }
-  uint32_t* ptr() const { return static_cast<uint32_t*>(d); }
 
   // every element must be non-negative and at most `words` words wide
   static bool fits(const std::vector<BigNumber>& v, int words) {
@@ -52,18 +48,24 @@ struct DeviceBatch {
     return true;
   }
 
+  void upload(const uint32_t* flat, int flat_words) {
+    if (count) DEVICE_CHECK(ipclb200_batch_upload(h, flat, flat_words));
+  }
+
   static std::shared_ptr<DeviceBatch> fromHost(const std::vector<BigNumber>& v,
                                                int words) {
     auto b = std::make_shared<DeviceBatch>(v.size(), words);
-    std::vector<uint32_t> flat;
+    PinnedBuffer& stage = PinnedBuffer::forThread();
+    uint32_t* flat = stage.get(v.size() * static_cast<std::size_t>(words));
     pack(v, words, flat);
-    if (!flat.empty()) DEVICE_CHECK(ipclb200_dev_upload(b->d, flat.data(), b->bytes()));
+    b->upload(flat, words);
     return b;
   }
 
   std::vector<BigNumber> toHost() const {
-    std::vector<uint32_t> flat(count * static_cast<std::size_t>(words));
-    if (!flat.empty()) DEVICE_CHECK(ipclb200_dev_download(flat.data(), d, bytes()));
+    PinnedBuffer& stage = PinnedBuffer::forThread();
+    uint32_t* flat = stage.get(count * static_cast<std::size_t>(words));
+    if (count) DEVICE_CHECK(ipclb200_batch_download(h, flat, words));
     return unpack(flat, count, words);
   }
 };

@@ -1,7 +1,10 @@
 // marshal.hpp -- vector<BigNumber> <-> flat little-endian limb buffers, the
 // data layout of the C ABI (include/ipcl_b200.h).  One pass, one memcpy per
-// element; replaces the per-chunk sub-vector copies and 8 x mod_dwords padding
-// buffers of ippMBModExp (ipcl/mod_exp.cpp:490-506,627-632).
+// element, OpenMP over the elements; replaces the per-chunk sub-vector copies
+// and 8 x mod_dwords padding buffers of ippMBModExp
+// (ipcl/mod_exp.cpp:490-506,627-632).  The flat side is a per-thread PINNED
+// staging buffer, so the copies to and from the GPUs are true DMA transfers
+// that overlap across devices.
 #ifndef IPCL_B200_SRC_MARSHAL_HPP_
 #define IPCL_B200_SRC_MARSHAL_HPP_
 
@@ -14,6 +17,20 @@
 namespace ipcl {
 namespace detail {
 
+// grow-only page-locked host buffer, one per calling thread (cudaHostAlloc
+// through the runtime; falls back to pageable memory if pinning fails)
+class PinnedBuffer {
+ public:
+  static PinnedBuffer& forThread();
+  uint32_t* get(std::size_t words);
+  ~PinnedBuffer();
+
+ private:
+  uint32_t* m_p = nullptr;
+  std::size_t m_words = 0;
+  bool m_pinned = false;
+};
+
 inline int maxWords(const std::vector<BigNumber>& v) {
   std::size_t w = 1;
   for (const auto& x : v)
@@ -23,25 +40,35 @@ inline int maxWords(const std::vector<BigNumber>& v) {
 
 // out: v.size() x words, zero padded.  Every element must be non-negative and
 // fit (callers reduce first).
-inline void pack(const std::vector<BigNumber>& v, int words,
-                 std::vector<uint32_t>& out) {
-  out.assign(v.size() * static_cast<std::size_t>(words), 0u);
-#pragma omp parallel for schedule(static) if (v.size() >= 4096)
+inline void pack(const std::vector<BigNumber>& v, int words, uint32_t* out) {
+  const std::size_t W = static_cast<std::size_t>(words);
+#pragma omp parallel for schedule(static) if (v.size() >= 1024)
   for (std::size_t i = 0; i < v.size(); i++) {
     const auto& w = v[i].words();
-    if (!w.empty())
-      std::memcpy(&out[i * static_cast<std::size_t>(words)], w.data(),
-                  w.size() * sizeof(uint32_t));
+    uint32_t* dst = out + i * W;
+    if (!w.empty()) std::memcpy(dst, w.data(), w.size() * sizeof(uint32_t));
+    if (w.size() < W) std::memset(dst + w.size(), 0, (W - w.size()) * sizeof(uint32_t));
   }
+}
+
+inline void pack(const std::vector<BigNumber>& v, int words,
+                 std::vector<uint32_t>& out) {
+  out.resize(v.size() * static_cast<std::size_t>(words));
+  pack(v, words, out.data());
+}
+
+inline std::vector<BigNumber> unpack(const uint32_t* flat, std::size_t count,
+                                     int words) {
+  std::vector<BigNumber> r(count);
+#pragma omp parallel for schedule(static) if (count >= 1024)
+  for (std::size_t i = 0; i < count; i++)
+    r[i].Set(flat + i * static_cast<std::size_t>(words), words, IppsBigNumPOS);
+  return r;
 }
 
 inline std::vector<BigNumber> unpack(const std::vector<uint32_t>& flat,
                                      std::size_t count, int words) {
-  std::vector<BigNumber> r(count);
-#pragma omp parallel for schedule(static) if (count >= 4096)
-  for (std::size_t i = 0; i < count; i++)
-    r[i].Set(&flat[i * static_cast<std::size_t>(words)], words, IppsBigNumPOS);
-  return r;
+  return unpack(flat.data(), count, words);
 }
 
 inline bool allEqual(const std::vector<BigNumber>& v) {

@@ -79,9 +79,7 @@ PlainText PrivateKey::decrypt(const CipherText& ct) const {
       detail::isClassWords(4 * pl)) {
     if (auto d_ct = ct.deviceBatch(4 * pl)) {
       auto d_pt = std::make_shared<detail::DeviceBatch>(ct_size, 2 * pl);
-      DEVICE_CHECK(ipclb200_decrypt_dev(m_dev->h, d_ct->ptr(), ct_size,
-                                        m_enable_crt ? 1 : 0, d_pt->ptr(),
-                                        ipclb200_stream()));
+      DEVICE_CHECK(ipclb200_decrypt_batch(m_dev->h, d_ct->h, m_enable_crt ? 1 : 0, d_pt->h));
       return PlainText(std::move(d_pt));
     }
   }

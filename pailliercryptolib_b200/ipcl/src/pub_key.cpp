@@ -245,13 +245,11 @@ CipherText PublicKey::encrypt(const PlainText& pt, bool make_secure) const {
         std::vector<uint32_t> f_r;
         flatRandoms(pt_size, f_r, r_words);
         d_r = std::make_shared<detail::DeviceBatch>(pt_size, r_words);
-        DEVICE_CHECK(ipclb200_dev_upload(d_r->d, f_r.data(), d_r->bytes()));
+        d_r->upload(f_r.data(), r_words);
       }
       auto d_ct = std::make_shared<detail::DeviceBatch>(pt_size, 2 * nl);
-      DEVICE_CHECK(ipclb200_encrypt_dev(dev, d_pt->ptr(), nl,
-                                        make_secure ? d_r->ptr() : nullptr,
-                                        r_words, pt_size, make_secure ? 1 : 0,
-                                        d_ct->ptr(), ipclb200_stream()));
+      DEVICE_CHECK(ipclb200_encrypt_batch(dev, d_pt->h, make_secure ? d_r->h : nullptr, 0,
+                                          make_secure ? 1 : 0, d_ct->h));
       return CipherText(*this, std::move(d_ct));
     }
   }
