@@ -8,20 +8,26 @@ ciphertexts that came out.  Key = the ISO/IEC 18033-6 primes the reference's
 own benchmark uses (benchmark/bench_cryptography.cpp:24-36).
 
   value : pairs/s with pt and r already resident in HBM (CUDA events on the
-          launching stream)
+          launching stream); under torchrun every rank has its own 65536-element
+          shard (weak scaling), value = all units / max-over-ranks time
   e2e   : the same step through the host-pointer C ABI (ipclb200_encrypt +
-          ipclb200_decrypt) from pinned host buffers, copies inside the timing
-  roofline : the decrypt modexp kernel against the measured IMAD.WIDE rate of
-          this GPU (the path is integer-ALU bound), plus
-          its HBM figures
+          ipclb200_decrypt) from pinned host buffers, copies inside the timing,
+          over all `steps`
+  roofline : the dominant kernel (two-digit CRT decrypt) against the measured
+          IMAD.WIDE rate of this GPU (the path is integer-ALU bound, SURVEY.md
+          section 8d): algorithmic fraction (generic w=5 modexp count) and the
+          fraction of the multiplies it actually executes
+  strong : ONE batch owned by rank 0 -- scatter -> encrypt -> decrypt -> gather
+          inside the timing (NCCL send/recv) -- for the 2048-bit/65536 headline
+          and BASELINE configs[3] (3072-bit key, 262144 elements); plus the same
+          batch through the library's own one-process multi-GPU path
+  configs : the other BASELINE configs (HE add / mul, raw modexp sweep, batch-8
+          round trip), each with roofline fractions and a full-buffer oracle
+          check of a sample
   cpu_baseline : the CPU restatement of the reference path (oracle/) on the
-          host cores, bounded sample
+          host cores, bounded sample (N = 1 only)
 
-Multi-GPU: one process per GPU (torchrun), every rank encrypts+decrypts its own
-65536-element shard -- independent units, no data-path collective -- weak
-scaling; value = all units / max-over-ranks time.
-
-`--impl reference` times the CPU path only (rank 0), see cpu_reference().
+`--impl reference` times the CPU path only (rank 0), see run_reference().
 """
 import argparse
 import json
@@ -44,6 +50,7 @@ PL = NL // 2                 # words of p, q
 METRIC = "Paillier encrypt+decrypt ops/sec @2048-bit, batch 64K"
 UNIT = "enc+dec pairs/s"
 
+
 # algorithmic work per unit, SURVEY.md section 8(d): W(k,e) = N(e) * M(k/32)
 def mont_macs(L):
     return 2 * L * L + L
@@ -53,25 +60,69 @@ def modexp_mults(e_bits):
     return e_bits + (e_bits + 4) // 5 + 32 + 2
 
 
-MAC_ENCRYPT = modexp_mults(KEY_BITS // 2) * mont_macs(2 * NL)      # 41.55 M
-MAC_DECRYPT = 2 * modexp_mults(KEY_BITS // 2) * mont_macs(NL)      # 20.85 M
+def mac_encrypt(key_bits):
+    return modexp_mults(key_bits // 2) * mont_macs(2 * key_bits // 32)
+
+
+def mac_decrypt(key_bits):
+    return 2 * modexp_mults(key_bits // 2) * mont_macs(key_bits // 32)
+
+
+def mac_modexp(mod_bits, exp_bits):
+    return modexp_mults(exp_bits) * mont_macs(mod_bits // 32)
+
+
+MAC_ENCRYPT = mac_encrypt(KEY_BITS)      # 41.55 M
+MAC_DECRYPT = mac_decrypt(KEY_BITS)      # 20.85 M
 BYTES_ENCRYPT = NL * 4 + RL * 4 + 2 * NL * 4     # pt + r in, ct out
 BYTES_DECRYPT = 2 * NL * 4 + NL * 4              # ct in, pt out
 
 
-def load_key():
+def sliding_counts(e, w=5):
+    """(squarings, multiplies) of the left-to-right sliding-window schedule the
+    kernels run for a shared exponent (host_common.hpp: build_schedule)"""
+    i, first, nsq, nmul = e.bit_length() - 1, True, 0, 0
+    while i >= 0:
+        if not (e >> i) & 1:
+            nsq += 1
+            i -= 1
+            continue
+        l = max(i - w + 1, 0)
+        while not (e >> l) & 1:
+            l += 1
+        if not first:
+            nsq += i - l + 1
+            nmul += 1
+        first = False
+        i = l - 1
+    return nsq, nmul
+
+
+def hensel_executed_macs(p, q):
+    """IMAD.WIDE the two-digit decrypt executes per ciphertext (mont_hensel.cuh):
+    a squaring is 4 LH^2 + LH, a multiply 5 LH^2, per side one squaring + 15
+    multiplies for the table, 16 LH^2 to enter and 2 LH^2 to leave"""
+    total = 0
+    for pr in (p, q):
+        LH = (pr.bit_length() + 31) // 32
+        nsq, nmul = sliding_counts(pr - 1)
+        total += (nsq + 1) * (4 * LH * LH + LH) + (nmul + 15) * 5 * LH * LH + 18 * LH * LH
+    return total
+
+
+def load_key(bits=KEY_BITS):
     with open(os.path.join(ROOT, "tests", "golden", "keys.json")) as f:
-        k = {a: int(b, 16) for a, b in json.load(f)[str(KEY_BITS)].items()}
+        k = {a: int(b, 16) for a, b in json.load(f)[str(bits)].items()}
     p, q = sorted((k["p"], k["q"]))
     return p, q, k["hs"]
 
 
-def synth_inputs(count, seed):
-    """uniform plaintexts in [0, 2^2046) (< n) and uniform 1024-bit randoms"""
+def synth_inputs(count, seed, nl=NL):
+    """uniform plaintexts in [0, 2^(bits-2)) (< n) and uniform bits/2-bit randoms"""
     from pailliercryptolib_b200.limbs import random_limbs
     rng = np.random.default_rng(seed)
-    pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
-    r = random_limbs(rng, count, RL)
+    pt = random_limbs(rng, count, nl, top_mask=0x3FFFFFFF)
+    r = random_limbs(rng, count, nl // 2)
     return pt, r
 
 
@@ -117,13 +168,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def cpu_reference(count, threads_note=True):
+def load_oracle(all_threads):
+    """the CPU oracle (test infrastructure; here only as the timed CPU baseline
+    and as the checker of the configs samples).  all_threads: torchrun exports
+    OMP_NUM_THREADS=1 to its workers -- the reference arm must use the cores the
+    box has, as ipcl's OMPUtilities::MaxThreads does (util.hpp:106-112)."""
+    if all_threads and "oracle" not in sys.modules:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    return orc
+
+
+def cpu_reference(count):
     """Times the CPU restatement of the reference path (oracle/) on `count`
     elements with all host threads: DJN encrypt then CRT decrypt, structured
     as the reference (generic fixed-window modexp per element; chunk-of-8
     multi-buffer AVX512-IFMA when the host has it).  Returns pairs/s etc."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as orc
+    orc = load_oracle(True)
     from pailliercryptolib_b200.limbs import to_limbs
     p, q, hs = load_key()
     n = p * q
@@ -155,11 +217,12 @@ def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.
     The genuine library cannot be built here (IPP-Crypto is not vendored and
     there is no network), so this is the labelled port under
-    oracle/.  Each step is a bounded sample of the 65536-element workload."""
+    oracle/.  Each step is the full 65536-element workload (--cpu-sample
+    bounds it for quick checks), on every host thread of the box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.cpu_sample
+    sample = args.cpu_sample if args.cpu_sample > 0 else BATCH
     times = []
     res = None
     for i in range(args.warmup + args.steps):
@@ -172,16 +235,16 @@ def run_reference(args):
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3 * BATCH / sample,
+        "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (52-bit limbs)" if "IFMA" in res["algo"] else "u32",
         "data": "synthetic",
         "config": {"workload": "2048-bit key, batch=65536 encrypt+decrypt "
                                "(DJN r=1024 bit, CRT decrypt)",
-                   "sample": "%d of 65536 elements per step" % sample},
+                   "elements_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"],
                          "kind": "port",
-                         "sample": "%d elements, %s" % (sample, res["algo"])},
+                         "sample": "%d elements per step, %s" % (sample, res["algo"])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,6 +263,226 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+# ---------------------------------------------------------------------------
+# strong scaling: one batch owned by rank 0
+# ---------------------------------------------------------------------------
+def strong_case(torch, dist, capi, sharding, dev, stream, world, rank, bits, total, steps):
+    """ONE `total`-element batch resident on rank 0's GPU: scatter plaintexts and
+    randoms -> encrypt -> decrypt -> gather the plaintexts back, all inside the
+    timed region.  Returns (ms per step max over ranks, scatter+gather ms)."""
+    from pailliercryptolib_b200.limbs import to_limbs
+    nl = bits // 32
+    p, q, hs = load_key(bits)
+    pk = capi.PubKey(to_limbs(p * q, nl), to_limbs(hs, 2 * nl), bits // 2)
+    sk = capi.PrivKey(to_limbs(p, nl // 2), to_limbs(q, nl // 2))
+    full_pt = full_r = None
+    if rank == 0:
+        pt_h, r_h = synth_inputs(total, seed=0x5712 + bits, nl=nl)
+        full_pt = torch.from_numpy(pt_h.view(np.int32)).to(dev)
+        full_r = torch.from_numpy(r_h.view(np.int32)).to(dev)
+    s, e = sharding.shard_range(total, world, rank)
+    cnt = e - s
+    d_ct = torch.empty((cnt, 2 * nl), dtype=torch.int32, device=dev)
+    d_dt = torch.empty((cnt, nl), dtype=torch.int32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(ev=None):
+        if ev:
+            ev[0].record()
+        loc_pt = sharding.scatter_rows(full_pt, total, nl, torch.int32, dev)
+        loc_r = sharding.scatter_rows(full_r, total, nl // 2, torch.int32, dev)
+        if ev:
+            ev[1].record()
+        pk.encrypt_dev(loc_pt.data_ptr(), nl, loc_r.data_ptr(), nl // 2, cnt,
+                       d_ct.data_ptr(), stream)
+        sk.decrypt_dev(d_ct.data_ptr(), cnt, d_dt.data_ptr(), stream)
+        if ev:
+            ev[2].record()
+        out = sharding.gather_rows(d_dt, total)
+        if ev:
+            ev[3].record()
+        return out
+
+    os.environ["IPCLB200_COMB_SYNC"] = "1"   # wide table before the timing starts
+    for _ in range(2):
+        out = one()
+    barrier()
+    if rank == 0:
+        assert torch.equal(out, full_pt), "strong: decrypt(encrypt(pt)) != pt"
+    ms, sg = [], []
+    for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
+        one(ev)
+        ev[3].synchronize()
+        ms.append(ev[0].elapsed_time(ev[3]))
+        sg.append(ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]))
+    barrier()
+    step_ms, sg_ms = sharding.max_over_ranks([float(np.mean(ms)), float(np.mean(sg))], dev)
+    del pk, sk
+    return step_ms, sg_ms
+
+
+def inproc_case(torch, capi, ndev, bits, total, steps):
+    """the same batch through the library's own multi-GPU path: ONE process,
+    ipclb200_init_devices(ndev), host-pointer encrypt + decrypt from pinned host
+    memory (every device copies its own contiguous block)"""
+    from pailliercryptolib_b200.limbs import to_limbs
+    nl = bits // 32
+    got = capi.init_devices(ndev)
+    p, q, hs = load_key(bits)
+    pk = capi.PubKey(to_limbs(p * q, nl), to_limbs(hs, 2 * nl), bits // 2)
+    sk = capi.PrivKey(to_limbs(p, nl // 2), to_limbs(q, nl // 2))
+    pt_h, r_h = synth_inputs(total, seed=0x1A + bits, nl=nl)
+    pin = lambda a: torch.from_numpy(a.view(np.int32)).pin_memory()
+    pt_pin, r_pin = pin(pt_h), pin(r_h)
+    ct_pin = torch.empty((total, 2 * nl), dtype=torch.int32).pin_memory()
+    dt_pin = torch.empty((total, nl), dtype=torch.int32).pin_memory()
+    u32 = lambda t: t.numpy().view(np.uint32)
+
+    def one():
+        pk.encrypt(u32(pt_pin), u32(r_pin), out=u32(ct_pin))
+        sk.decrypt(u32(ct_pin), out=u32(dt_pin))
+
+    os.environ["IPCLB200_COMB_SYNC"] = "1"
+    for _ in range(2):
+        one()
+    assert np.array_equal(u32(dt_pin), pt_h), "inproc: round trip failed"
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    del pk, sk
+    return got, ms
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE configs (rank 0, devices of the library's active set)
+# ---------------------------------------------------------------------------
+def run_configs(torch, capi, peak_mac, quick):
+    from pailliercryptolib_b200.limbs import random_limbs, to_limbs
+    orc = load_oracle(True)
+    fast = orc.have_ifma()
+    out = []
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0xC0F)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def cuda(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+
+    def host(t):
+        return t.cpu().numpy().view(np.uint32)
+
+    # ---- configs[2]: HE add (ct+ct) and HE mul (ct*pt), 2048-bit key, 65536 ----
+    p, q, hs = load_key()
+    n = p * q
+    nsq = to_limbs(n * n, 2 * NL)
+    pk = capi.PubKey(to_limbs(n, NL), to_limbs(hs, 2 * NL), KEY_BITS // 2)
+    count = 16384 if quick else BATCH
+    pt, r = synth_inputs(count, 0xADD)
+    d_a = torch.empty((count, 2 * NL), dtype=torch.int32, device=dev)
+    pk.encrypt_dev(cuda(pt).data_ptr(), NL, cuda(r).data_ptr(), RL, count, d_a.data_ptr(),
+                   stream)
+    torch.cuda.synchronize()
+    d_b = d_a.flip(0).contiguous()
+    d_o = torch.empty_like(d_a)
+    ms = timed(lambda: capi.modmul_dev(d_a.data_ptr(), d_b.data_ptr(), nsq, count,
+                                       d_o.data_ptr(), stream), 5)
+    S = 2048
+    ok = bool(np.array_equal(host(d_o[:S]), orc.modmul(host(d_a[:S]), host(d_b[:S]), nsq)))
+    macs = 2 * mont_macs(2 * NL)
+    out.append({"config": "2048-bit key, batch=%d HE add (ct+ct)" % count, "ms": ms,
+                "ops_per_s": count / ms * 1e3, "kernel": "modmul_kernel<16,8>",
+                "roofline": {"frac": count * macs / (ms * 1e-3) / peak_mac,
+                             "executed_frac": count * 2 * 2 * (2 * NL) ** 2 / (ms * 1e-3) / peak_mac,
+                             "hbm_gbs": count * 3 * 2 * NL * 4 / (ms * 1e-3) / 1e9},
+                "oracle_check": {"elements": S, "ok": ok}})
+    for ebits, label in ((32, "32-bit plaintexts"), (2048, "2048-bit plaintexts")):
+        ew = max(1, ebits // 32)
+        cnt = count if ebits == 32 else (4096 if quick else 16384)
+        e = random_limbs(rng, cnt, ew)
+        d_e = cuda(e)
+        ms = timed(lambda: capi.modexp_dev(d_a.data_ptr(), d_e.data_ptr(), nsq, ew, ebits, cnt,
+                                           d_o.data_ptr(), stream), 2)
+        S2 = 1024
+        want = (orc.modexp_mb8(host(d_a[:S2]), e[:S2], nsq) if fast else
+                orc.modexp(host(d_a[:S2]), e[:S2], nsq[None, :], shared_mod=True))
+        ok = bool(np.array_equal(host(d_o[:S2]), want))
+        macs = mac_modexp(2 * KEY_BITS, ebits)
+        nprod = ebits + ebits // 5 + 30
+        out.append({"config": "2048-bit key, batch=%d HE mul (ct*pt), %s" % (cnt, label),
+                    "ms": ms, "ops_per_s": cnt / ms * 1e3, "kernel": "modexp_kernel<16,8>",
+                    "roofline": {"frac": cnt * macs / (ms * 1e-3) / peak_mac,
+                                 "executed_frac": cnt * nprod * 2 * (2 * NL) ** 2 / (ms * 1e-3) / peak_mac},
+                    "oracle_check": {"elements": S2, "ok": ok}})
+    del pk
+    # ---- configs[4]: raw modexp sweep (k-bit modulus, k-bit exponent) -----------
+    for k in (1024, 2048, 3072, 4096):
+        L = k // 32
+        mod = random_limbs(rng, 1, L)
+        mod[0, 0] |= 1
+        mod[0, -1] |= 0x80000000
+        for lg in ((10, 14) if quick else (10, 14, 18)):
+            cnt = 1 << lg
+            base = random_limbs(rng, cnt, L)
+            base[:, -1] &= 0x7FFFFFFF
+            e = random_limbs(rng, cnt, L)
+            d_base, d_e = cuda(base), cuda(e)
+            d_out = torch.empty_like(d_base)
+            reps = 1 if (lg == 18 and k >= 3072) else 2
+            ms = timed(lambda: capi.modexp_dev(d_base.data_ptr(), d_e.data_ptr(), mod[0], L, k,
+                                               cnt, d_out.data_ptr(), stream), reps)
+            S3 = min(cnt, 1024 if k <= 2048 else 256)
+            want = (orc.modexp_mb8(base[:S3], e[:S3], mod[0]) if fast and k <= 4096 else
+                    orc.modexp(base[:S3], e[:S3], mod, shared_mod=True))
+            ok = bool(np.array_equal(host(d_out[:S3]), want))
+            macs = mac_modexp(k, k)
+            nprod = k + k // 5 + 30
+            out.append({"config": "raw modexp %d-bit, batch=2^%d" % (k, lg), "ms": ms,
+                        "ops_per_s": cnt / ms * 1e3,
+                        "roofline": {"frac": cnt * macs / (ms * 1e-3) / peak_mac,
+                                     "executed_frac": cnt * nprod * 2 * L * L / (ms * 1e-3) / peak_mac,
+                                     "hbm_gbs": cnt * 3 * L * 4 / (ms * 1e-3) / 1e9},
+                        "oracle_check": {"elements": S3, "ok": ok}})
+            del d_base, d_e, d_out
+    # ---- configs[0]: 1024-bit key, batch 8 round trip (host-pointer C ABI) ------
+    p1, q1, hs1 = load_key(1024)
+    n1 = p1 * q1
+    pk1 = capi.PubKey(to_limbs(n1, 32), to_limbs(hs1, 64), 512)
+    sk1 = capi.PrivKey(to_limbs(p1, 16), to_limbs(q1, 16))
+    pt8 = random_limbs(rng, 8, 32, top_mask=0x3FFFFFFF)
+    r8 = random_limbs(rng, 8, 16)
+    ct8 = pk1.encrypt(pt8, r8)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ct8 = pk1.encrypt(pt8, r8)
+        dt8 = sk1.decrypt(ct8)
+    ms = (time.perf_counter() - t0) * 1e3 / 20
+    ok = bool(np.array_equal(ct8, orc.encrypt(to_limbs(n1, 32), to_limbs(hs1, 64), pt8, r8))
+              and np.array_equal(dt8, pt8))
+    out.append({"config": "1024-bit key, batch=8 encrypt->decrypt round trip "
+                          "(host-pointer C ABI, wall clock)", "ms": ms,
+                "ops_per_s": 8 / ms * 1e3, "oracle_check": {"elements": 8, "ok": ok}})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,9 +490,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-sample", type=int, default=16384,
-                    help="elements of the workload timed on the CPU")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="elements of the workload timed on the CPU (0 = 65536 for "
+                         "--impl reference, 16384 for the cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="smaller side measurements")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -218,7 +505,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pailliercryptolib_b200 import capi
+    from pailliercryptolib_b200 import capi, sharding
     from pailliercryptolib_b200.limbs import to_limbs
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,8 +564,16 @@ def main():
     # ---- integer roofline denominator, measured live on this GPU -----------
     peak_mac, _ = capi.int_peak()
 
-    # ---- warm-up (also builds the comb table and sizes the workspaces) -----
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up: also builds the fixed-base table.  The wide (16-bit window,
+    # 2.1 GB) table is normally built on a side stream while the first calls use
+    # the 17 MB one; here the bench waits for it so that every timed step runs on
+    # the steady-state table.  Its build time is reported below.
+    os.environ["IPCLB200_COMB_SYNC"] = "1"
+    t_tab0 = time.perf_counter()
+    step_dev()
+    torch.cuda.synchronize()
+    table_build_ms = (time.perf_counter() - t_tab0) * 1e3
+    for _ in range(max(args.warmup, 3) - 1):
         step_dev()
     torch.cuda.synchronize()
     assert torch.equal(d_dt, d_pt), "decrypt(encrypt(pt)) != pt on the device"
@@ -301,39 +596,57 @@ def main():
     t_wall1 = time.perf_counter()
     launches = capi.launch_count() - launches0
     step_ms = float(np.sum(enc_ms) + np.sum(dec_ms)) / args.steps
-    # ---- timed: end to end through the host-pointer C ABI ------------------
+    # ---- timed: end to end through the host-pointer C ABI, all steps ---------
     step_e2e()   # warm
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         step_e2e()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert np.array_equal(dt_pin.numpy().view(np.uint32), pt_h), "e2e round trip failed"
 
-    from pailliercryptolib_b200 import sharding
-    # the scatter/gather a single-owner batch would need (north_star: "NCCL
-    # only for the trivial scatter/gather"); outside the timed region
-    sg_ms = None
-    if world > 1:
-        full = d_pt.repeat(world, 1) if rank == 0 else None
-        for _ in range(2):
-            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
-            barrier()
-            e0.record()
-            loc = sharding.scatter_rows(full, B * world, NL, torch.int32, dev)
-            back = sharding.gather_rows(loc, B * world)
-            e1.record()
-            e1.synchronize()
-            sg_ms = e0.elapsed_time(e1)
-        del full, loc, back
     step_ms, e2e_ms, enc_mean, dec_mean = sharding.max_over_ranks(
         [step_ms, e2e_ms, float(np.mean(enc_ms)), float(np.mean(dec_ms))], dev)
-    if sg_ms is not None:
-        sg_ms = sharding.max_over_ranks([sg_ms], dev)[0]
+    del d_ct, d_dt, flush
+
+    # ---- strong scaling: one batch owned by rank 0 ---------------------------
+    strong = None
+    if not args.no_strong:
+        ssteps = max(1, min(args.steps, 5))
+        strong = {"note": "ONE batch resident on rank 0's GPU; scatter (NCCL send/recv) -> "
+                          "encrypt -> decrypt -> gather inside the timing, max over ranks"}
+        ms, sg = strong_case(torch, dist, capi, sharding, dev, stream, world, rank,
+                             KEY_BITS, BATCH, ssteps)
+        strong["headline_64k"] = {
+            "workload": "2048-bit key, ONE batch of 65536", "ms_per_step": ms,
+            "value": BATCH / (ms * 1e-3), "unit": UNIT, "scatter_gather_ms": sg,
+            "steps": ssteps}
+        c4 = 65536 if args.quick else 262144
+        ms, sg = strong_case(torch, dist, capi, sharding, dev, stream, world, rank,
+                             3072, c4, max(1, min(ssteps, 3)))
+        strong["config4_3072bit"] = {
+            "workload": "3072-bit key, ONE batch of %d (BASELINE configs[3])" % c4,
+            "ms_per_step": ms, "value": c4 / (ms * 1e-3), "unit": UNIT,
+            "scatter_gather_ms": sg, "steps": max(1, min(ssteps, 3))}
+    barrier()
+    if rank == 0 and not args.no_strong:
+        # the library's own one-process path over the same GPUs
+        ndev = min(world, torch.cuda.device_count())
+        got, ms = inproc_case(torch, capi, ndev, KEY_BITS, BATCH, max(1, min(args.steps, 5)))
+        strong["inproc_64k"] = {
+            "workload": "2048-bit key, ONE batch of 65536 in pinned host memory, ONE "
+                        "process driving %d GPU(s) through ipclb200_init_devices + the "
+                        "host-pointer C ABI (copies inside the timing)" % got,
+            "devices": got, "ms_per_step": ms, "value": BATCH / (ms * 1e-3), "unit": UNIT}
+        capi.init_devices(1) if local == 0 else None
+    configs = None
+    if rank == 0 and not args.no_configs:
+        torch.cuda.set_device(local)
+        configs = run_configs(torch, capi, peak_mac, args.quick or world > 1)
+    barrier()
 
     if rank == 0:
         total = B * world
@@ -350,24 +663,35 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get("decrypt_crt_kernel_dram_bytes")
+                traffic = json.load(f)
         except Exception:
             pass
         comb_w = int(os.environ.get("IPCLB200_COMB_WINDOW", "16"))
         comb_products = (KEY_BITS // 2 + comb_w - 1) // comb_w - 1 + 3
         ach = B * MAC_DECRYPT / dec_s / 1e12
+        exec_macs = hensel_executed_macs(p, q)
         roofline = {
-            "kernel": "decrypt_crt_kernel<16,4> (2 x 2048-bit-modulus, "
-                      "1024-bit-exponent modexp per ciphertext)",
+            "kernel": "decrypt_hensel_kernel<16,2> + crt_combine_kernel (per ciphertext two "
+                      "1024-bit-exponent modexps mod p^2, q^2 in two-digit arithmetic)",
             "bound": "int32_alu",
             "achieved": ach, "peak": peak_mac / 1e12, "unit": "TMAC32/s",
             "frac": ach / (peak_mac / 1e12),
+            "executed_frac": B * exec_macs / dec_s / peak_mac,
+            "note": "frac counts the generic algorithm of SURVEY 8d (full-width w=5 "
+                    "windowed modexp, 20.85 M MAC32 per ciphertext) and exceeds 1 because "
+                    "the kernel works in half-width digits mod p^2 (%.2f M MAC32 executed); "
+                    "executed_frac is the share of the IMAD.WIDE issue rate the executed "
+                    "multiplies take" % (exec_macs / 1e6),
             "peak_source": "measured live: dependent IMAD.WIDE.U32 chains on all "
                            "SMs (ipclb200_int_peak)",
             "algorithmic_mac32_per_unit": MAC_DECRYPT,
+            "executed_mac32_per_unit": exec_macs,
             "units_per_launch": B,
             "launch_ms": dec_mean,
-            "traffic": traffic,
+            "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+            "traffic_source": (traffic or {}).get(
+                "source", "none") + " (static: read from profiles/ncu_traffic.json, "
+                                    "not measured in this run)",
             "hbm": {"achieved": B * BYTES_DECRYPT / dec_s / 1e9, "peak": hbm_peak,
                     "unit": "GB/s",
                     "frac": B * BYTES_DECRYPT / dec_s / 1e9 / hbm_peak,
@@ -395,10 +719,13 @@ def main():
                                    "(DJN r=1024 bit, CRT decrypt), 1xB200 per rank",
                        "batch_per_gpu": B, "key_bits": KEY_BITS,
                        "l2": "256 MB flush written between timed iterations",
-                       "parallelism": "shard per GPU, no data-path collective"},
+                       "parallelism": "shard per GPU, no data-path collective",
+                       "fixed_base_table": "16-bit windows, 2.1 GB, built once per key in "
+                                           "warm-up (first step incl. build: %.0f ms)"
+                                           % table_build_ms},
             "encrypt_per_s": total / enc_s, "decrypt_per_s": total / dec_s,
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT,
-                    "ms_per_step": e2e_ms,
+                    "ms_per_step": e2e_ms, "steps": args.steps,
                     "h2d_bytes_per_step": B * (NL + RL + 2 * NL) * 4,
                     "d2h_bytes_per_step": B * (2 * NL + NL) * 4},
             "gpu_launches": launches,
@@ -406,14 +733,17 @@ def main():
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
-        if sg_ms is not None:
-            line["nccl_scatter_gather_ms"] = sg_ms
+        if strong is not None:
+            line["strong"] = strong
+        if configs is not None:
+            line["configs"] = configs
         if not args.no_cpu_baseline and world == 1:
-            res = cpu_reference(args.cpu_sample)
+            sample = args.cpu_sample if args.cpu_sample > 0 else 16384
+            res = cpu_reference(sample)
             line["cpu_baseline"] = {
                 "value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"],
                 "kind": "port",
-                "sample": "%d of 65536 elements, %s" % (args.cpu_sample, res["algo"]),
+                "sample": "%d of 65536 elements, %s" % (sample, res["algo"]),
                 "encrypt_per_s": res["encrypt_per_s"],
                 "decrypt_per_s": res["decrypt_per_s"]}
         emit_json(line)
