@@ -162,11 +162,49 @@ def build_cpp_tests(force=False):
     return CPP_TEST_BIN
 
 
+REFERENCE = "/root/reference"
+REF_UNIT_BIN = os.path.join(CPP_TEST_DIR, "_build", "ref_unit_tests")
+REF_EXAMPLES = ("example_encrypt_decrypt", "example_add_mul", "example_hybridmode")
+
+
+def ref_example_bin(name):
+    return os.path.join(CPP_TEST_DIR, "_build", "ref_" + name)
+
+
+def build_reference_programs(force=False):
+    """The reference's OWN test and example sources, compiled UNMODIFIED from
+    where they lie under /root/reference against this repo's ipcl:: headers and
+    libipcl.so (gtest comes from tests/cpp/gtest_shim).  Only the binaries land
+    in the repo (tests/cpp/_build/, git-ignored, shipped to the GPU box); no
+    reference source is copied.  Without /root/reference (the GPU box) the
+    prebuilt binaries are used as they are."""
+    if not os.path.isdir(os.path.join(REFERENCE, "test")):
+        return None
+    build_ipcl()
+    inc = ["-I", os.path.join(PKG, "ipcl", "include"), "-I", os.path.join(ROOT, "include")]
+    link = ["-L", LIBDIR, "-lipcl", "-lipcl_b200",
+            "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"]
+    os.makedirs(os.path.dirname(REF_UNIT_BIN), exist_ok=True)
+    tsrc = [os.path.join(REFERENCE, "test", f) for f in
+            ("main.cpp", "test_cryptography.cpp", "test_ops.cpp", "test_serialization.cpp")]
+    shim = os.path.join(CPP_TEST_DIR, "gtest_shim")
+    if force or not _newer(REF_UNIT_BIN, tsrc + [IPCL_LIB, os.path.join(shim, "gtest", "gtest.h")]):
+        _run(["g++", "-O2", "-std=c++17", "-fopenmp", "-I", shim] + inc +
+             ["-o", REF_UNIT_BIN] + tsrc + link)
+    for name in REF_EXAMPLES:
+        src = os.path.join(REFERENCE, "example", name + ".cpp")
+        out = ref_example_bin(name)
+        if force or not _newer(out, [src, IPCL_LIB]):
+            _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", out, src] + link)
+    return REF_UNIT_BIN
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_ipcl(force)
     build_oracle(force)
     build_cpp_tests(force)
+    build_reference_programs(force)
 
 
 if __name__ == "__main__":
