@@ -525,8 +525,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side barrier for the phases in which rank 0 alone drives every GPU
+        # of the box: a NCCL barrier would keep a spinning kernel on the other
+        # ranks' GPUs and time-slice with rank 0's work there
+        cpu_group = dist.new_group(backend="gloo")
     capi.init(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream().cuda_stream
@@ -644,7 +649,8 @@ def main():
             "scatter_gather_ms": sg, "steps": max(1, min(ssteps, 3))}
     barrier()
     if rank == 0 and not args.no_strong:
-        # the library's own one-process path over the same GPUs
+        # the library's own one-process path over the same GPUs (the other ranks
+        # wait in a CPU barrier, their GPUs are idle)
         ndev = min(world, torch.cuda.device_count())
         got, ms = inproc_case(torch, capi, ndev, KEY_BITS, BATCH, max(1, min(args.steps, 5)))
         strong["inproc_64k"] = {
@@ -657,7 +663,9 @@ def main():
     if rank == 0 and not args.no_configs:
         torch.cuda.set_device(local)
         configs = run_configs(torch, capi, peak_mac, args.quick or world > 1)
-    barrier()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         total = B * world

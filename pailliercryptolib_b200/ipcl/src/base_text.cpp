@@ -30,41 +30,78 @@ std::vector<BigNumber> rotated(const std::vector<BigNumber>& v, int shift) {
   return out;
 }
 
+// Page-locked staging buffers are kept in a process-wide pool that is never
+// destroyed: a thread borrows one on first use and hands it back when it ends.
+// Nothing is freed at process exit, where the CUDA runtime may already be gone.
+namespace {
+struct PinnedSlab {
+  uint32_t* p = nullptr;
+  std::size_t words = 0;
+  bool pinned = false;
+};
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<PinnedSlab> idle;
+};
+PinnedPool& pinnedPool() {
+  static PinnedPool* pool = new PinnedPool;  // intentionally leaked
+  return *pool;
+}
+void releaseSlab(PinnedSlab& s) {
+  if (!s.p) return;
+  if (s.pinned)
+    ipclb200_host_free(s.p);
+  else
+    std::free(s.p);
+  s = PinnedSlab{};
+}
+}  // namespace
+
 PinnedBuffer& PinnedBuffer::forThread() {
   thread_local PinnedBuffer b;
   return b;
 }
 
 uint32_t* PinnedBuffer::get(std::size_t words) {
-  if (words > m_words) {
-    if (m_p) {
-      if (m_pinned)
-        ipclb200_host_free(m_p);
-      else
-        std::free(m_p);
-      m_p = nullptr;
-    }
-    const std::size_t want = words + words / 4 + 1024;
-    void* p = nullptr;
-    if (ipclb200_host_alloc(want * sizeof(uint32_t), &p) == 0) {
-      m_pinned = true;
-    } else {
-      p = std::malloc(want * sizeof(uint32_t));
-      ERROR_CHECK(p != nullptr, "out of host memory");
-      m_pinned = false;
-    }
-    m_p = static_cast<uint32_t*>(p);
-    m_words = want;
+  if (words <= m_words) return m_p;
+  PinnedSlab cur{m_p, m_words, m_pinned};
+  m_p = nullptr;
+  m_words = 0;
+  {
+    // a large enough idle slab?
+    PinnedPool& pool = pinnedPool();
+    std::lock_guard<std::mutex> lk(pool.mu);
+    for (std::size_t i = 0; i < pool.idle.size(); i++)
+      if (pool.idle[i].words >= words) {
+        PinnedSlab got = pool.idle[i];
+        pool.idle.erase(pool.idle.begin() + static_cast<std::ptrdiff_t>(i));
+        if (cur.p) pool.idle.push_back(cur);
+        m_p = got.p;
+        m_words = got.words;
+        m_pinned = got.pinned;
+        return m_p;
+      }
   }
+  releaseSlab(cur);
+  const std::size_t want = words + words / 4 + 1024;
+  void* p = nullptr;
+  if (ipclb200_host_alloc(want * sizeof(uint32_t), &p) == 0) {
+    m_pinned = true;
+  } else {
+    p = std::malloc(want * sizeof(uint32_t));
+    ERROR_CHECK(p != nullptr, "out of host memory");
+    m_pinned = false;
+  }
+  m_p = static_cast<uint32_t*>(p);
+  m_words = want;
   return m_p;
 }
 
 PinnedBuffer::~PinnedBuffer() {
   if (!m_p) return;
-  if (m_pinned)
-    ipclb200_host_free(m_p);
-  else
-    std::free(m_p);
+  PinnedPool& pool = pinnedPool();
+  std::lock_guard<std::mutex> lk(pool.mu);
+  pool.idle.push_back(PinnedSlab{m_p, m_words, m_pinned});
 }
 
 bool deviceResidentEnabled() {
