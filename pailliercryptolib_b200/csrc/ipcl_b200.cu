@@ -464,6 +464,7 @@ struct CombTable {
 // device-side state of a public key on one device
 struct PubDev {
   Dev* dev = nullptr;
+  int dev_id = -1;  // valid after ipclb200_shutdown() has deleted *dev
   std::shared_ptr<DevModulus> msq;
   uint32_t* d_const = nullptr;  // [nR (L) | hs_m (L) | n as exponent (nl)]
   uint8_t* d_sched_n = nullptr;
@@ -472,10 +473,12 @@ struct PubDev {
   std::vector<CombTable> retired;  // replaced tables, freed with the key
 };
 
+// dev == nullptr: the runtime was shut down (terminateContext) before the key
+// died; the device memory is still valid and is freed, only the accounting is gone
 void free_comb(Dev* dev, CombTable& t) {
   if (t.d) {
     cudaFree(t.d);
-    if (t.full) {
+    if (t.full && dev) {
       std::lock_guard<std::mutex> lk(dev->mu);
       dev->comb_bytes -= std::min(dev->comb_bytes, t.bytes);
     }
@@ -484,8 +487,17 @@ void free_comb(Dev* dev, CombTable& t) {
   t = CombTable{};
 }
 
+// the Dev a key replica was created on, or nullptr if ipclb200_shutdown() has
+// deleted it since (the reference's examples call terminateContext() before
+// their keys and texts go out of scope)
+Dev* live_dev(Dev* dev, int id) {
+  if (id < 0 || id >= kMaxDevices) return nullptr;
+  return g.dev[id].load() == dev ? dev : nullptr;
+}
+
 struct PrivDev {
   Dev* dev = nullptr;
+  int dev_id = -1;
   std::shared_ptr<DevModulus> mp2, mq2, mnsq;
   uint32_t* d_const = nullptr;
   uint8_t* d_sched = nullptr;
@@ -519,14 +531,15 @@ struct ipclb200_pubkey {
   ~ipclb200_pubkey() {
     for (auto& pd : dev) {
       if (!pd) continue;
-      if (g.dev[pd->dev->id].load() != pd->dev) continue;  // after shutdown
-      cudaSetDevice(pd->dev->id);
+      Dev* live = live_dev(pd->dev, pd->dev_id);
+      cudaSetDevice(pd->dev_id);
       cudaDeviceSynchronize();
       if (pd->d_const) cudaFree(pd->d_const);
       if (pd->d_sched_n) cudaFree(pd->d_sched_n);
-      free_comb(pd->dev, pd->cur);
-      free_comb(pd->dev, pd->next);
-      for (auto& t : pd->retired) free_comb(pd->dev, t);
+      free_comb(live, pd->cur);
+      free_comb(live, pd->next);
+      for (auto& t : pd->retired) free_comb(live, t);
+      cudaGetLastError();
     }
   }
 };
@@ -557,8 +570,7 @@ struct ipclb200_privkey {
   ~ipclb200_privkey() {
     for (auto& sd : dev) {
       if (!sd) continue;
-      if (g.dev[sd->dev->id].load() != sd->dev) continue;  // after shutdown
-      cudaSetDevice(sd->dev->id);
+      cudaSetDevice(sd->dev_id);
       cudaDeviceSynchronize();
       if (sd->d_const) cudaFree(sd->d_const);
       if (sd->d_sched) cudaFree(sd->d_sched);
@@ -582,6 +594,7 @@ int pub_dev(const ipclb200_pubkey* pk_c, Dev* dev, PubDev** out) {
   if (!slot) {
     std::unique_ptr<PubDev> pd(new PubDev);
     pd->dev = dev;
+    pd->dev_id = dev->id;
     TRY(make_modulus(dev, pk->nsq, pk->L, &pd->msq));
     CUDA_TRY(cudaSetDevice(dev->id));
     CUDA_TRY(cudaMalloc(&pd->d_const, pk->h_const.size() * sizeof(uint32_t)));
@@ -594,6 +607,7 @@ int pub_dev(const ipclb200_pubkey* pk_c, Dev* dev, PubDev** out) {
     }
     slot = std::move(pd);
   }
+  slot->dev = dev;  // a Dev re-created after ipclb200_shutdown(): same device memory
   *out = slot.get();
   return 0;
 }
@@ -605,6 +619,7 @@ int priv_dev(const ipclb200_privkey* sk_c, Dev* dev, PrivDev** out) {
   if (!slot) {
     std::unique_ptr<PrivDev> sd(new PrivDev);
     sd->dev = dev;
+    sd->dev_id = dev->id;
     TRY(make_modulus(dev, sk->psq, sk->L, &sd->mp2));
     TRY(make_modulus(dev, sk->qsq, sk->L, &sd->mq2));
     TRY(make_modulus(dev, sk->nsq, sk->Lnsq, &sd->mnsq));
@@ -629,6 +644,7 @@ int priv_dev(const ipclb200_privkey* sk_c, Dev* dev, PrivDev** out) {
 #endif
     slot = std::move(sd);
   }
+  slot->dev = dev;
   *out = slot.get();
   return 0;
 }
@@ -1054,13 +1070,38 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
   }
   int rows = 8;
   if (const char* e = getenv("IPCLB200_HENSEL_ROWS")) rows = atoi(e);
+  // Lane layout by the number of (ciphertext, side) tasks: the multiplier pipe
+  // needs about 8 warps per SM, so a small batch spreads every task over more
+  // lanes (fewer limbs per lane) until the launch fills the GPU -- the same idea
+  // as the wide layouts of the generic kernels.  spread 0/1/2 = T x1 / x2 / x4.
+  int spread = 0;
+  {
+    const size_t tasks = 2 * count;
+    const size_t fill = (size_t)op.dev->sms * 8 * 32;  // lanes of 8 warps per SM
+    const size_t t0 = pl == 64 ? 4 : 2;
+    if (tasks * t0 < fill) spread = 1;
+    if (tasks * t0 * 2 < fill) spread = 2;
+    if (const char* e = getenv("IPCLB200_HENSEL_SPREAD")) spread = atoi(e);
+    const char* w = getenv("IPCLB200_WIDE");
+    if (w && w[0] == '0') spread = 0;
+  }
   switch (pl) {
-    case 16: FH(8, 2, 3, 8) break;
-    case 32:
-      if (rows == 4) FH(16, 2, 3, 4) else if (rows == 16) FH(16, 2, 3, 16) else FH(16, 2, 3, 8)
+    case 16:
+      if (spread >= 1) FH(4, 4, 3, 8) else FH(8, 2, 3, 8)
       break;
-    case 48: FH(24, 2, 2, 8) break;
-    case 64: FH(16, 4, 3, 8) break;
+    case 32:
+      if (spread >= 2) FH(4, 8, 3, 8)
+      else if (spread == 1) FH(8, 4, 3, 8)
+      else if (rows == 4) FH(16, 2, 3, 4)
+      else if (rows == 16) FH(16, 2, 3, 16)
+      else FH(16, 2, 3, 8)
+      break;
+    case 48:
+      if (spread >= 1) FH(12, 4, 3, 8) else FH(24, 2, 2, 8)
+      break;
+    case 64:
+      if (spread >= 1) FH(8, 8, 3, 8) else FH(16, 4, 3, 8)
+      break;
     default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel: unsupported prime width");
   }
 #undef FH
@@ -1287,6 +1328,7 @@ struct ipclb200_batch {
   int words = 0;
   std::vector<Shard> shards;
   std::vector<uint32_t*> d;
+  std::vector<int> dev_ids;
 };
 
 namespace {
@@ -1955,6 +1997,7 @@ int ipclb200_batch_alloc(size_t count, int words, ipclb200_batch** out) {
     CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(16, sh.count * (size_t)words * 4),
                              sh.dev->stream));
     b->d.push_back(p);
+    b->dev_ids.push_back(sh.dev->id);
   }
   *out = b.release();
   return 0;
@@ -1964,13 +2007,13 @@ void ipclb200_batch_free(ipclb200_batch* b) {
   if (!b) return;
   DeviceGuard guard;
   for (size_t i = 0; i < b->d.size(); i++) {
-    Dev* d = b->shards[i].dev;
-    bool alive = false;
-    for (auto& slot : g.dev)
-      if (slot.load() == d) alive = true;
-    if (!alive) continue;  // after shutdown: the pool is gone
-    cudaSetDevice(d->id);
-    cudaFreeAsync(b->d[i], d->stream);
+    Dev* d = live_dev(b->shards[i].dev, b->dev_ids[i]);
+    cudaSetDevice(b->dev_ids[i]);
+    if (d)
+      cudaFreeAsync(b->d[i], d->stream);
+    else
+      cudaFree(b->d[i]);  // after ipclb200_shutdown(): no stream left to order on
+    cudaGetLastError();
   }
   delete b;
 }
