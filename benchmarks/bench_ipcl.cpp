@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ipcl/ipcl.hpp"
@@ -114,6 +115,37 @@ int main(int argc, char** argv) {
       }
       report("Pipeline_2enc_add_mul32_dec", dsize, us);
     }
+  }
+  // concurrent callers on one key pair (the reference's contract: encrypt and
+  // decrypt are called from 4 OpenMP threads, test/test_cryptography.cpp:45-57).
+  // Every call runs on its own stream of the library: four callers of a small
+  // batch should take little longer than one.
+  {
+    ipcl::PublicKey pk(n, n_length, true);
+    ipcl::PrivateKey sk(pk, P_BN, Q_BN);
+    pk.setHS(HS_BN);
+    const size_t dsize = 256;
+    std::vector<BigNumber> v(dsize);
+    for (size_t i = 0; i < dsize; i++) v[i] = P_BN - BigNumber((unsigned int)(i * 1024));
+    ipcl::PlainText pt(v);
+    auto caller = [&](int reps) {
+      for (int r = 0; r < reps; r++) {
+        ipcl::CipherText ct = pk.encrypt(pt);
+        ipcl::PlainText dt = sk.decrypt(ct);
+        if (dt.getElement(dsize - 1) != v[dsize - 1]) std::abort();
+      }
+    };
+    caller(3);
+    const int reps = 10;
+    double us1 = time_us([&] { caller(reps); }, 3, 0.3);
+    double us4 = time_us([&] {
+      std::vector<std::thread> th;
+      for (int t = 0; t < 4; t++) th.emplace_back(caller, reps);
+      for (auto& t : th) t.join();
+    }, 3, 0.3);
+    std::printf("{\"benchmark\": \"Concurrent_enc_dec_batch256\", \"one_caller_us\": %.1f, "
+                "\"four_callers_us\": %.1f, \"ratio\": %.2f}\n", us1 / reps, us4 / reps,
+                us4 / us1);
   }
   ipcl::terminateContext();
   return 0;

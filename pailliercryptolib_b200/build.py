@@ -150,7 +150,7 @@ def build_cpp_tests(force=False):
                        "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
     bench_src = os.path.join(ROOT, "benchmarks", "bench_ipcl.cpp")
     if os.path.exists(bench_src) and (force or not _newer(BENCH_BIN, [bench_src, IPCL_LIB])):
-        _run(["g++", "-O2", "-std=c++17", "-I", CPP_TEST_DIR] + inc + ["-o", BENCH_BIN, bench_src,
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-I", CPP_TEST_DIR] + inc + ["-o", BENCH_BIN, bench_src,
               "-L", LIBDIR, "-lipcl", "-lipcl_b200",
               "-Wl,-rpath,$ORIGIN/../../../pailliercryptolib_b200/lib"])
     shim_src = os.path.join(CPP_TEST_DIR, "bn_shim.cpp")

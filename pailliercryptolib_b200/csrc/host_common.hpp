@@ -201,6 +201,37 @@ inline void hensel_side_block(const Limbs& p, const Limbs& psq, const Limbs& hp,
   hbn::to_words(nhp, out + (size_t)9 * pl, pl);
 }
 
+// Lane layout of decrypt_hensel_kernel for a batch: spread 0/1/2 = one
+// (ciphertext, side) task over T0, 2*T0, 4*T0 lanes.  A launch is `rounds` of the
+// resident warps; a full round costs F (pipe bound, 12 warps per SM), a partial
+// one max(L, F * fill) -- L = latency of one task alone.  L and F measured at a
+// 2048-bit key (profiles/r02_hensel_small_batches.md), only their ratios matter:
+//   limbs per lane   16: L 10.0  F 20.0     8: L 5.7  F 11.0     4: L 3.95  F 6.5
+// Predicts the measured optimum at every batch size from 16 to 65536.
+inline int pick_hensel_spread(size_t count, int pl, int sms) {
+  static const double kL[3] = {10.0, 5.7, 3.95}, kF[3] = {20.0, 11.0, 6.5};
+  const int t0 = pl == 64 ? 4 : 2;          // lanes per task at spread 0
+  const int first = pl == 16 ? 1 : 0;       // pl = 16 starts at 8 limbs per lane
+  const int nspread = pl == 32 ? 3 : 2;     // instantiated layouts
+  const double resident = 12.0 * sms;       // warps
+  int best = 0;
+  double best_t = -1;
+  for (int sp = 0; sp < nspread; sp++) {
+    const int T = t0 << sp;
+    const double chunks = 2.0 * (double)((count + (32 / T) - 1) / (32 / T));
+    const double full = (double)(size_t)(chunks / resident);
+    const double fill = chunks / resident - full;
+    const double L = kL[first + sp], F = kF[first + sp];
+    double t = full * F;
+    if (fill > 0) t += (L > F * fill ? L : F * fill);
+    if (best_t < 0 || t < best_t) {
+      best_t = t;
+      best = sp;
+    }
+  }
+  return best;
+}
+
 // ---------------------------------------------------------------------------
 // per-modulus Montgomery constants (host side)
 // ---------------------------------------------------------------------------

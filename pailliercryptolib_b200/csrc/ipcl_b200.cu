@@ -1070,20 +1070,17 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
   }
   int rows = 8;
   if (const char* e = getenv("IPCLB200_HENSEL_ROWS")) rows = atoi(e);
-  // Lane layout by the number of (ciphertext, side) tasks: the multiplier pipe
-  // needs about 8 warps per SM, so a small batch spreads every task over more
-  // lanes (fewer limbs per lane) until the launch fills the GPU -- the same idea
-  // as the wide layouts of the generic kernels.  spread 0/1/2 = T x1 / x2 / x4.
-  int spread = 0;
+  // Lane layout by batch size: a small batch spreads every (ciphertext, side)
+  // task over more lanes (fewer limbs per lane) so that the launch fills the
+  // GPU and a task's latency shrinks -- the idea of the wide layouts of the
+  // generic kernels, chosen by the cost model of pick_hensel_spread().
+  int spread = pick_hensel_spread(count, pl, op.dev->sms);
   {
-    const size_t tasks = 2 * count;
-    const size_t fill = (size_t)op.dev->sms * 8 * 32;  // lanes of 8 warps per SM
-    const size_t t0 = pl == 64 ? 4 : 2;
-    if (tasks * t0 < fill) spread = 1;
-    if (tasks * t0 * 2 < fill) spread = 2;
     if (const char* e = getenv("IPCLB200_HENSEL_SPREAD")) spread = atoi(e);
     const char* w = getenv("IPCLB200_WIDE");
     if (w && w[0] == '0') spread = 0;
+    if (w && w[0] == '1') spread = 2;
+    if (w && w[0] == '2') spread = 1;
   }
   switch (pl) {
     case 16:

@@ -16,6 +16,8 @@ namespace detail {
 // a batch of big integers in HBM, count x words little-endian limbs -- the
 // layout of the C ABI (src/device_batch.hpp)
 struct DeviceBatch;
+// the flat host image of a device batch (src/marshal.hpp)
+struct FlatImage;
 }  // namespace detail
 
 class BaseText {
@@ -69,10 +71,16 @@ class BaseText {
   void ensureHost() const;
   // before a mutation: materialise, then forget the (now stale) device copy
   void hostOnly();
+  // single-element reads of a device-resident text: ONE download of the flat
+  // limb image, a BigNumber only for the element asked for (the reference
+  // copies the whole vector<BigNumber>, base_text.cpp:102)
+  const detail::FlatImage* flatImage() const;
+  BigNumber elementFromFlat(std::size_t idx) const;
 
   mutable std::vector<BigNumber> m_texts;
   std::size_t m_size = 0;
   mutable std::shared_ptr<detail::DeviceBatch> m_dev;
+  mutable std::shared_ptr<detail::FlatImage> m_flat;
   mutable std::atomic<bool> m_host_valid{true};
 };
 

@@ -30,32 +30,75 @@ std::vector<BigNumber> rotated(const std::vector<BigNumber>& v, int shift) {
   return out;
 }
 
-// Page-locked staging buffers are kept in a process-wide pool that is never
-// destroyed: a thread borrows one on first use and hands it back when it ends.
-// Nothing is freed at process exit, where the CUDA runtime may already be gone.
+// ---- pool of page-locked slabs (marshal.hpp) -------------------------------------
 namespace {
-struct PinnedSlab {
-  uint32_t* p = nullptr;
-  std::size_t words = 0;
-  bool pinned = false;
-};
-struct PinnedPool {
+struct SlabPool {
   std::mutex mu;
-  std::vector<PinnedSlab> idle;
+  std::vector<HostSlab> idle;
+  std::size_t idle_words = 0;
 };
-PinnedPool& pinnedPool() {
-  static PinnedPool* pool = new PinnedPool;  // intentionally leaked
+SlabPool& slabPool() {
+  static SlabPool* pool = new SlabPool;  // intentionally leaked, see marshal.hpp
   return *pool;
 }
-void releaseSlab(PinnedSlab& s) {
+constexpr std::size_t kMaxIdleWords = (std::size_t)1 << 28;  // 1 GB kept for reuse
+void freeSlab(HostSlab& s) {
   if (!s.p) return;
   if (s.pinned)
     ipclb200_host_free(s.p);
   else
     std::free(s.p);
-  s = PinnedSlab{};
+  s = HostSlab{};
 }
 }  // namespace
+
+HostSlab acquireHostSlab(std::size_t words) {
+  if (words == 0) words = 4;
+  {
+    SlabPool& pool = slabPool();
+    std::lock_guard<std::mutex> lk(pool.mu);
+    // best fit among the idle slabs (not more than 2x too large)
+    std::size_t best = pool.idle.size();
+    for (std::size_t i = 0; i < pool.idle.size(); i++)
+      if (pool.idle[i].words >= words && pool.idle[i].words <= 2 * words + 4096 &&
+          (best == pool.idle.size() || pool.idle[i].words < pool.idle[best].words))
+        best = i;
+    if (best != pool.idle.size()) {
+      HostSlab got = pool.idle[best];
+      pool.idle.erase(pool.idle.begin() + static_cast<std::ptrdiff_t>(best));
+      pool.idle_words -= got.words;
+      return got;
+    }
+  }
+  HostSlab s;
+  const std::size_t want = words + words / 8 + 1024;
+  void* p = nullptr;
+  if (ipclb200_host_alloc(want * sizeof(uint32_t), &p) == 0) {
+    s.pinned = true;
+  } else {
+    p = std::malloc(want * sizeof(uint32_t));
+    ERROR_CHECK(p != nullptr, "out of host memory");
+    s.pinned = false;
+  }
+  s.p = static_cast<uint32_t*>(p);
+  s.words = want;
+  return s;
+}
+
+void returnHostSlab(HostSlab& s) {
+  if (!s.p) return;
+  SlabPool& pool = slabPool();
+  {
+    std::lock_guard<std::mutex> lk(pool.mu);
+    if (pool.idle_words + s.words <= kMaxIdleWords) {
+      pool.idle.push_back(s);
+      pool.idle_words += s.words;
+      s = HostSlab{};
+      return;
+    }
+  }
+  freeSlab(s);
+}
 
 PinnedBuffer& PinnedBuffer::forThread() {
   thread_local PinnedBuffer b;
@@ -63,45 +106,20 @@ PinnedBuffer& PinnedBuffer::forThread() {
 }
 
 uint32_t* PinnedBuffer::get(std::size_t words) {
-  if (words <= m_words) return m_p;
-  PinnedSlab cur{m_p, m_words, m_pinned};
-  m_p = nullptr;
-  m_words = 0;
-  {
-    // a large enough idle slab?
-    PinnedPool& pool = pinnedPool();
-    std::lock_guard<std::mutex> lk(pool.mu);
-    for (std::size_t i = 0; i < pool.idle.size(); i++)
-      if (pool.idle[i].words >= words) {
-        PinnedSlab got = pool.idle[i];
-        pool.idle.erase(pool.idle.begin() + static_cast<std::ptrdiff_t>(i));
-        if (cur.p) pool.idle.push_back(cur);
-        m_p = got.p;
-        m_words = got.words;
-        m_pinned = got.pinned;
-        return m_p;
-      }
+  if (words > m_slab.words) {
+    returnHostSlab(m_slab);
+    m_slab = acquireHostSlab(words);
   }
-  releaseSlab(cur);
-  const std::size_t want = words + words / 4 + 1024;
-  void* p = nullptr;
-  if (ipclb200_host_alloc(want * sizeof(uint32_t), &p) == 0) {
-    m_pinned = true;
-  } else {
-    p = std::malloc(want * sizeof(uint32_t));
-    ERROR_CHECK(p != nullptr, "out of host memory");
-    m_pinned = false;
-  }
-  m_p = static_cast<uint32_t*>(p);
-  m_words = want;
-  return m_p;
+  return m_slab.p;
 }
 
+// thread exit: the slab goes back to the pool (nothing is freed at process exit)
 PinnedBuffer::~PinnedBuffer() {
-  if (!m_p) return;
-  PinnedPool& pool = pinnedPool();
+  if (!m_slab.p) return;
+  SlabPool& pool = slabPool();
   std::lock_guard<std::mutex> lk(pool.mu);
-  pool.idle.push_back(PinnedSlab{m_p, m_words, m_pinned});
+  pool.idle.push_back(m_slab);
+  pool.idle_words += m_slab.words;
 }
 
 bool deviceResidentEnabled() {
@@ -126,13 +144,36 @@ void BaseText::ensureHost() const {
   if (m_host_valid.load(std::memory_order_acquire)) return;
   std::lock_guard<std::mutex> lk(g_materialize_mutex);
   if (m_host_valid.load(std::memory_order_relaxed)) return;
-  m_texts = m_dev->toHost();
+  if (m_flat)
+    m_texts = detail::unpack(m_flat->slab.p, m_flat->count, m_flat->words);
+  else
+    m_texts = m_dev->toHost();
   m_host_valid.store(true, std::memory_order_release);
+}
+
+// the flat host image of a device-resident text: ONE download, no BigNumber
+// objects; single-element accessors read from it
+const detail::FlatImage* BaseText::flatImage() const {
+  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  if (!m_flat && m_dev) {
+    auto img = std::make_shared<detail::FlatImage>(m_dev->count, m_dev->words);
+    m_dev->downloadFlat(img->slab.p);
+    m_flat = std::move(img);
+  }
+  return m_flat.get();
+}
+
+BigNumber BaseText::elementFromFlat(std::size_t idx) const {
+  const detail::FlatImage* f = flatImage();
+  BigNumber r;
+  r.Set(f->element(idx), f->words, IppsBigNumPOS);
+  return r;
 }
 
 void BaseText::hostOnly() {
   ensureHost();
   m_dev.reset();
+  m_flat.reset();
 }
 
 std::shared_ptr<detail::DeviceBatch> BaseText::deviceBatch(int words) const {
@@ -178,6 +219,7 @@ BaseText::BaseText(std::vector<BigNumber>&& bn_v)
 BaseText::BaseText(const BaseText& bt) : m_size(bt.m_size) {
   std::lock_guard<std::mutex> lk(g_materialize_mutex);
   m_dev = bt.m_dev;
+  m_flat = bt.m_flat;
   const bool valid = bt.m_host_valid.load();
   if (valid) m_texts = bt.m_texts;
   m_host_valid.store(valid);
@@ -188,6 +230,7 @@ BaseText& BaseText::operator=(const BaseText& other) {
     std::lock_guard<std::mutex> lk(g_materialize_mutex);
     m_size = other.m_size;
     m_dev = other.m_dev;
+    m_flat = other.m_flat;
     const bool valid = other.m_host_valid.load();
     if (valid)
       m_texts = other.m_texts;
@@ -206,30 +249,38 @@ BigNumber& BaseText::operator[](const std::size_t idx) {
 
 BigNumber BaseText::getElement(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElement");
-  ensureHost();
+  if (!m_host_valid.load(std::memory_order_acquire)) return elementFromFlat(idx);
   return m_texts[idx];
 }
 
 std::vector<uint32_t> BaseText::getElementVec(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElementVec");
-  ensureHost();
   std::vector<uint32_t> words;
-  m_texts[idx].num2vec(words);
+  if (!m_host_valid.load(std::memory_order_acquire))
+    elementFromFlat(idx).num2vec(words);
+  else
+    m_texts[idx].num2vec(words);
   return words;
 }
 
 std::string BaseText::getElementHex(const std::size_t& idx) const {
   TEXT_INDEX_CHECK(idx, "getElementHex");
-  ensureHost();
   std::string hex;
-  m_texts[idx].num2hex(hex);
+  if (!m_host_valid.load(std::memory_order_acquire))
+    elementFromFlat(idx).num2hex(hex);
+  else
+    m_texts[idx].num2hex(hex);
   return hex;
 }
 
 std::vector<BigNumber> BaseText::getChunk(const std::size_t& start,
                                           const std::size_t& size) const {
   ERROR_CHECK(start + size <= m_size, "BaseText: getChunk parameter is incorrect");
-  ensureHost();
+  if (!m_host_valid.load(std::memory_order_acquire)) {
+    std::vector<BigNumber> out(size);
+    for (std::size_t i = 0; i < size; i++) out[i] = elementFromFlat(start + i);
+    return out;
+  }
   return {m_texts.begin() + static_cast<std::ptrdiff_t>(start),
           m_texts.begin() + static_cast<std::ptrdiff_t>(start + size)};
 }
@@ -251,6 +302,7 @@ void BaseText::remove(const std::size_t pos, const std::size_t length) {
 
 void BaseText::clear() {
   m_dev.reset();
+  m_flat.reset();
   m_texts.clear();
   m_host_valid.store(true);
   m_size = 0;

@@ -62,6 +62,10 @@ struct DeviceBatch {
     return b;
   }
 
+  void downloadFlat(uint32_t* dst) const {
+    if (count) DEVICE_CHECK(ipclb200_batch_download(h, dst, words));
+  }
+
   std::vector<BigNumber> toHost() const {
     PinnedBuffer& stage = PinnedBuffer::forThread();
     uint32_t* flat = stage.get(count * static_cast<std::size_t>(words));

@@ -17,8 +17,29 @@
 namespace ipcl {
 namespace detail {
 
-// grow-only page-locked host buffer, one per calling thread (cudaHostAlloc
-// through the runtime; falls back to pageable memory if pinning fails)
+// Page-locked host memory comes from a process-wide pool of slabs that is never
+// torn down (at process exit the CUDA runtime may already be gone): acquire a
+// slab of at least `words` words, hand it back when done.  Falls back to
+// pageable memory if pinning fails.
+struct HostSlab {
+  uint32_t* p = nullptr;
+  std::size_t words = 0;
+  bool pinned = false;
+};
+HostSlab acquireHostSlab(std::size_t words);
+void returnHostSlab(HostSlab& s);
+
+// a slab for the duration of a scope (flat operands / results of one call)
+struct ScopedSlab {
+  HostSlab s;
+  explicit ScopedSlab(std::size_t words) : s(acquireHostSlab(words)) {}
+  ~ScopedSlab() { returnHostSlab(s); }
+  ScopedSlab(const ScopedSlab&) = delete;
+  ScopedSlab& operator=(const ScopedSlab&) = delete;
+  uint32_t* data() const { return s.p; }
+};
+
+// grow-only staging buffer of the calling thread (pack / unpack go through it)
 class PinnedBuffer {
  public:
   static PinnedBuffer& forThread();
@@ -26,9 +47,26 @@ class PinnedBuffer {
   ~PinnedBuffer();
 
  private:
-  uint32_t* m_p = nullptr;
-  std::size_t m_words = 0;
-  bool m_pinned = false;
+  HostSlab m_slab;
+};
+
+// the flat host image of a device batch (count x words limbs): what a text
+// keeps when a caller reads single elements -- no BigNumber is built for the
+// elements nobody looks at
+struct FlatImage {
+  HostSlab slab;
+  std::size_t count = 0;
+  int words = 0;
+  FlatImage(std::size_t count_, int words_)
+      : slab(acquireHostSlab(count_ * static_cast<std::size_t>(words_))),
+        count(count_),
+        words(words_) {}
+  ~FlatImage() { returnHostSlab(slab); }
+  FlatImage(const FlatImage&) = delete;
+  FlatImage& operator=(const FlatImage&) = delete;
+  const uint32_t* element(std::size_t i) const {
+    return slab.p + i * static_cast<std::size_t>(words);
+  }
 };
 
 inline int maxWords(const std::vector<BigNumber>& v) {

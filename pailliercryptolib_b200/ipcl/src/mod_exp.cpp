@@ -79,28 +79,33 @@ std::vector<BigNumber> ippModExp(const std::vector<BigNumber>& base,
   }
   const bool shared_base = n > 1 && detail::allEqual(*bp);
 
-  std::vector<uint32_t> fb, fe, fm, fo(n * static_cast<std::size_t>(mod_words));
+  // flat operands and results in page-locked slabs: the copies to and from the
+  // GPU(s) are DMA transfers
+  const std::size_t MW = static_cast<std::size_t>(mod_words);
+  const std::size_t EW = static_cast<std::size_t>(exp_words);
+  detail::ScopedSlab fb((shared_base ? 1 : n) * MW), fe((shared_exp ? 1 : n) * EW),
+      fm((shared_mod ? 1 : n) * MW), fo(n * MW);
   if (shared_base) {
-    detail::pack({(*bp)[0]}, mod_words, fb);
+    detail::pack({(*bp)[0]}, mod_words, fb.data());
     flags |= IPCLB200_SHARED_BASE;
   } else {
-    detail::pack(*bp, mod_words, fb);
+    detail::pack(*bp, mod_words, fb.data());
   }
   if (shared_exp) {
-    detail::pack({exp[0]}, exp_words, fe);
+    detail::pack({exp[0]}, exp_words, fe.data());
     flags |= IPCLB200_SHARED_EXP;
   } else {
-    detail::pack(exp, exp_words, fe);
+    detail::pack(exp, exp_words, fe.data());
   }
   if (shared_mod) {
-    detail::pack({mod[0]}, mod_words, fm);
+    detail::pack({mod[0]}, mod_words, fm.data());
     flags |= IPCLB200_SHARED_MOD;
   } else {
-    detail::pack(mod, mod_words, fm);
+    detail::pack(mod, mod_words, fm.data());
   }
   DEVICE_CHECK(ipclb200_modexp(fb.data(), fe.data(), fm.data(), mod_words,
                                exp_words, n, flags, fo.data()));
-  return detail::unpack(fo, n, mod_words);
+  return detail::unpack(fo.data(), n, mod_words);
 }
 
 BigNumber ippModExp(const BigNumber& base, const BigNumber& exp,
@@ -154,14 +159,15 @@ std::vector<BigNumber> modMul(const std::vector<BigNumber>& a,
       rb[i] = b[i] % mod;
       pb = &rb;
     }
-  std::vector<uint32_t> fa, fb, fm, fo(n * static_cast<std::size_t>(words));
-  detail::pack(*pa, words, fa);
-  detail::pack(*pb, words, fb);
-  detail::pack({mod}, words, fm);
+  const std::size_t W = static_cast<std::size_t>(words);
+  detail::ScopedSlab fa(n * W), fb(pb->size() * W), fm(W), fo(n * W);
+  detail::pack(*pa, words, fa.data());
+  detail::pack(*pb, words, fb.data());
+  detail::pack({mod}, words, fm.data());
   unsigned flags = (b.size() == 1 && n > 1) ? IPCLB200_SHARED_B : 0u;
   DEVICE_CHECK(ipclb200_modmul(fa.data(), fb.data(), fm.data(), words, n, flags,
                                fo.data()));
-  return detail::unpack(fo, n, words);
+  return detail::unpack(fo.data(), n, words);
 }
 
 }  // namespace ipcl

@@ -109,10 +109,11 @@ static void device_decrypt(ipclb200_privkey* h, int pl, const BigNumber& nsq,
       cp = &reduced;
     }
   }
-  std::vector<uint32_t> f_ct, f_pt(n * 2 * static_cast<std::size_t>(pl));
-  detail::pack(*cp, cw, f_ct);
+  detail::ScopedSlab f_ct(n * static_cast<std::size_t>(cw)),
+      f_pt(n * 2 * static_cast<std::size_t>(pl));
+  detail::pack(*cp, cw, f_ct.data());
   DEVICE_CHECK(ipclb200_decrypt(h, f_ct.data(), n, use_crt, f_pt.data()));
-  plaintext = detail::unpack(f_pt, n, 2 * pl);
+  plaintext = detail::unpack(f_pt.data(), n, 2 * pl);
 }
 
 void PrivateKey::decryptRAW(std::vector<BigNumber>& plaintext,

@@ -211,14 +211,16 @@ std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
   ipclb200_pubkey* dev = deviceKey();
   std::vector<BigNumber> reduced;
   const std::vector<BigNumber>& pp = reducedPlain(pt, *m_n, nl, reduced);
-  std::vector<uint32_t> f_pt, f_r, f_ct(sz * 2 * static_cast<std::size_t>(nl));
-  detail::pack(pp, nl, f_pt);
+  std::vector<uint32_t> f_r;
+  detail::ScopedSlab f_pt(sz * static_cast<std::size_t>(nl)),
+      f_ct(sz * 2 * static_cast<std::size_t>(nl));
+  detail::pack(pp, nl, f_pt.data());
   int r_words = 0;
   if (make_secure) flatRandoms(sz, f_r, r_words);
   DEVICE_CHECK(ipclb200_encrypt(dev, f_pt.data(), nl,
                                 make_secure ? f_r.data() : nullptr, r_words, sz,
                                 make_secure ? 1 : 0, f_ct.data()));
-  return detail::unpack(f_ct, sz, 2 * nl);
+  return detail::unpack(f_ct.data(), sz, 2 * nl);
 }
 
 CipherText PublicKey::encrypt(const PlainText& pt, bool make_secure) const {
