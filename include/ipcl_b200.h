@@ -207,8 +207,10 @@ int ipclb200_host_free(void* p);
 /* ---- batches sharded over the active devices ---------------------------------
  * count x words limbs in HBM, split into contiguous blocks over the devices of
  * ipclb200_init_devices (one block on one device otherwise).  Every operation
- * on a batch is enqueued on the library stream of each shard's device; nothing
- * waits until batch_download / batch_sync.  Batches of equal count are sharded
+ * on a batch is enqueued on the calling thread's own stream of each shard's
+ * device, ordered by an event per shard behind whatever touched the operands
+ * before -- threads working on different batches overlap -- and nothing waits
+ * until batch_download / batch_sync.  Batches of equal count are sharded
  * identically, so element i of every operand lives on the same device.
  *   batch_upload / download : host buffer of count x h_words (h_words <= words,
  *                             zero padded / truncated per element)
@@ -230,6 +232,10 @@ int ipclb200_batch_shard(const ipclb200_batch* b, int shard, int* device, void**
 int ipclb200_batch_upload(ipclb200_batch* b, const uint32_t* h, int h_words);
 int ipclb200_batch_download(const ipclb200_batch* b, uint32_t* h, int h_words);
 int ipclb200_batch_sync(const ipclb200_batch* b);
+/* batch_shard hands out the calling thread's stream, already ordered behind the
+ * work enqueued on the shard; a caller that enqueues kernels of its own there
+ * calls batch_touch afterwards so that later library calls wait for them */
+int ipclb200_batch_touch(const ipclb200_batch* b, int shard, void* stream);
 int ipclb200_batch_scatter(ipclb200_batch* b, const uint32_t* d_src);
 int ipclb200_batch_gather(const ipclb200_batch* b, uint32_t* d_dst);
 int ipclb200_encrypt_batch(const ipclb200_pubkey* pk, const ipclb200_batch* pt,

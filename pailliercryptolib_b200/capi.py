@@ -43,6 +43,7 @@ EXPORTS = [
     "ipclb200_batch_sync", "ipclb200_batch_scatter", "ipclb200_batch_gather",
     "ipclb200_encrypt_batch", "ipclb200_decrypt_batch", "ipclb200_modmul_batch",
     "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
+    "ipclb200_batch_touch",
 ]
 
 

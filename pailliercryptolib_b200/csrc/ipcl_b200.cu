@@ -275,6 +275,26 @@ struct Op {
   ~Op() { close(); }
 };
 
+// The stream batch operations of the calling thread run on (one per thread and
+// device, never returned: threads are few).  Batches carry an event, so work
+// of different threads on different batches overlaps while every batch sees its
+// own operations in order.
+cudaStream_t thread_stream(Dev* d) {
+  thread_local cudaStream_t streams[kMaxDevices] = {};
+  thread_local Dev* owners[kMaxDevices] = {};
+  if (owners[d->id] != d || !streams[d->id]) {
+    cudaSetDevice(d->id);
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      return d->stream;
+    }
+    streams[d->id] = s;
+    owners[d->id] = d;
+  }
+  return streams[d->id];
+}
+
 // restores the caller's current device when a multi-device call returns
 struct DeviceGuard {
   int prev = -1;
@@ -1326,9 +1346,30 @@ struct ipclb200_batch {
   std::vector<Shard> shards;
   std::vector<uint32_t*> d;
   std::vector<int> dev_ids;
+  // per shard: recorded behind the last operation that touched the shard (as
+  // input or output), on whatever stream that was; the next operation waits for it
+  std::vector<cudaEvent_t> last;
 };
 
 namespace {
+
+// the calling thread's stream for shard i, ordered behind everything enqueued
+// on the operand batches so far
+int batch_stream(std::initializer_list<const ipclb200_batch*> operands, size_t i, Dev* dev,
+                 cudaStream_t* out) {
+  cudaStream_t s = thread_stream(dev);
+  CUDA_TRY(cudaSetDevice(dev->id));
+  for (const ipclb200_batch* b : operands)
+    if (b) CUDA_TRY(cudaStreamWaitEvent(s, b->last[i], 0));
+  *out = s;
+  return 0;
+}
+int batch_touch(std::initializer_list<const ipclb200_batch*> operands, size_t i,
+                cudaStream_t s) {
+  for (const ipclb200_batch* b : operands)
+    if (b) CUDA_TRY(cudaEventRecord(b->last[i], s));
+  return 0;
+}
 
 bool same_plan(const ipclb200_batch* a, const ipclb200_batch* b) {
   if (a->count != b->count || a->shards.size() != b->shards.size()) return false;
@@ -1991,10 +2032,14 @@ int ipclb200_batch_alloc(size_t count, int words, ipclb200_batch** out) {
   for (auto& sh : b->shards) {
     uint32_t* p = nullptr;
     CUDA_TRY(cudaSetDevice(sh.dev->id));
-    CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(16, sh.count * (size_t)words * 4),
-                             sh.dev->stream));
+    cudaStream_t s = thread_stream(sh.dev);
+    CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(16, sh.count * (size_t)words * 4), s));
+    cudaEvent_t ev = nullptr;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, s));
     b->d.push_back(p);
     b->dev_ids.push_back(sh.dev->id);
+    b->last.push_back(ev);
   }
   *out = b.release();
   return 0;
@@ -2006,10 +2051,14 @@ void ipclb200_batch_free(ipclb200_batch* b) {
   for (size_t i = 0; i < b->d.size(); i++) {
     Dev* d = live_dev(b->shards[i].dev, b->dev_ids[i]);
     cudaSetDevice(b->dev_ids[i]);
-    if (d)
-      cudaFreeAsync(b->d[i], d->stream);
-    else
+    if (d) {
+      cudaStream_t s = thread_stream(d);
+      cudaStreamWaitEvent(s, b->last[i], 0);
+      cudaFreeAsync(b->d[i], s);
+    } else {
       cudaFree(b->d[i]);  // after ipclb200_shutdown(): no stream left to order on
+    }
+    cudaEventDestroy(b->last[i]);
     cudaGetLastError();
   }
   delete b;
@@ -2027,7 +2076,13 @@ int ipclb200_batch_shard(const ipclb200_batch* b, int shard, int* device, void**
   if (d_ptr) *d_ptr = b->d[shard];
   if (begin) *begin = b->shards[shard].begin;
   if (count) *count = b->shards[shard].count;
-  if (stream) *stream = (void*)b->shards[shard].dev->stream;
+  if (stream) {
+    // the calling thread's stream, ordered behind what was enqueued on the shard;
+    // call ipclb200_batch_touch after enqueuing work of your own on it
+    cudaStream_t s = nullptr;
+    TRY(batch_stream({b}, (size_t)shard, b->shards[shard].dev, &s));
+    *stream = (void*)s;
+  }
   return 0;
 }
 
@@ -2042,16 +2097,18 @@ int ipclb200_batch_upload(ipclb200_batch* b, const uint32_t* h, int h_words) {
     pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
   }
+  std::vector<cudaStream_t> ss(b->shards.size());
   for (size_t i = 0; i < b->shards.size(); i++) {
     const Shard& sh = b->shards[i];
-    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    TRY(batch_stream({b}, i, sh.dev, &ss[i]));
     TRY(upload_padded(b->d[i], h + sh.begin * (size_t)h_words, h_words, b->words, sh.count,
-                      sh.dev->stream));
+                      ss[i]));
+    TRY(batch_touch({b}, i, ss[i]));
   }
   if (pinned)
-    for (auto& sh : b->shards) {
-      CUDA_TRY(cudaSetDevice(sh.dev->id));
-      CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+    for (size_t i = 0; i < b->shards.size(); i++) {
+      CUDA_TRY(cudaSetDevice(b->shards[i].dev->id));
+      CUDA_TRY(cudaStreamSynchronize(ss[i]));
     }
   return 0;
 }
@@ -2060,15 +2117,17 @@ int ipclb200_batch_download(const ipclb200_batch* b, uint32_t* h, int h_words) {
   if (!b || !h || h_words <= 0 || h_words > b->words)
     return fail(IPCLB200_ERR_BAD_ARG, "batch_download: bad argument");
   DeviceGuard guard;
+  std::vector<cudaStream_t> ss(b->shards.size());
   for (size_t i = 0; i < b->shards.size(); i++) {
     const Shard& sh = b->shards[i];
-    CUDA_TRY(cudaSetDevice(sh.dev->id));
+    TRY(batch_stream({b}, i, sh.dev, &ss[i]));
     TRY(download_padded(h + sh.begin * (size_t)h_words, b->d[i], h_words, b->words, sh.count,
-                        sh.dev->stream));
+                        ss[i]));
+    TRY(batch_touch({b}, i, ss[i]));
   }
-  for (auto& sh : b->shards) {
-    CUDA_TRY(cudaSetDevice(sh.dev->id));
-    CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+  for (size_t i = 0; i < b->shards.size(); i++) {
+    CUDA_TRY(cudaSetDevice(b->shards[i].dev->id));
+    CUDA_TRY(cudaStreamSynchronize(ss[i]));
   }
   return 0;
 }
@@ -2076,11 +2135,19 @@ int ipclb200_batch_download(const ipclb200_batch* b, uint32_t* h, int h_words) {
 int ipclb200_batch_sync(const ipclb200_batch* b) {
   if (!b) return 0;
   DeviceGuard guard;
-  for (auto& sh : b->shards) {
-    CUDA_TRY(cudaSetDevice(sh.dev->id));
-    CUDA_TRY(cudaStreamSynchronize(sh.dev->stream));
+  for (size_t i = 0; i < b->shards.size(); i++) {
+    CUDA_TRY(cudaSetDevice(b->shards[i].dev->id));
+    CUDA_TRY(cudaEventSynchronize(b->last[i]));
   }
   return 0;
+}
+
+// after enqueuing work of your own on the stream ipclb200_batch_shard returned
+int ipclb200_batch_touch(const ipclb200_batch* b, int shard, void* stream) {
+  if (!b || shard < 0 || shard >= (int)b->shards.size())
+    return fail(IPCLB200_ERR_BAD_ARG, "batch_touch: bad argument");
+  CUDA_TRY(cudaSetDevice(b->shards[shard].dev->id));
+  return batch_touch({b}, (size_t)shard, (cudaStream_t)stream);
 }
 
 // scatter: a contiguous device buffer (count x words, on the device of shard 0)
@@ -2098,33 +2165,39 @@ static int batch_exchange(ipclb200_batch* b, uint32_t* d_flat, bool scatter) {
       return fail(IPCLB200_ERR_BAD_ARG,
                   "batch scatter/gather: buffer is not on the first device");
   }
+  std::vector<cudaStream_t> ss(b->shards.size());
+  for (size_t i = 0; i < b->shards.size(); i++)
+    TRY(batch_stream({b}, i, b->shards[i].dev, &ss[i]));
   CUDA_TRY(cudaSetDevice(root->id));
   if (scatter)
     CUDA_TRY(cudaMemcpyAsync(b->d[0], d_flat, b->shards[0].count * W * 4,
-                             cudaMemcpyDeviceToDevice, root->stream));
+                             cudaMemcpyDeviceToDevice, ss[0]));
   else
     CUDA_TRY(cudaMemcpyAsync(d_flat, b->d[0], b->shards[0].count * W * 4,
-                             cudaMemcpyDeviceToDevice, root->stream));
-  if (b->shards.size() == 1) return 0;
-  std::lock_guard<std::mutex> lk(g_nccl.mu);
-  TRY(nccl_comms(b->shards));
-  NCCL_TRY(g_nccl.GroupStart());
-  for (size_t i = 1; i < b->shards.size(); i++) {
-    const Shard& sh = b->shards[i];
-    uint32_t* at_root = d_flat + sh.begin * W;
-    if (scatter) {
-      NCCL_TRY(g_nccl.Send(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
-                           root->stream));
-      NCCL_TRY(g_nccl.Recv(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i],
-                           sh.dev->stream));
-    } else {
-      NCCL_TRY(g_nccl.Send(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i],
-                           sh.dev->stream));
-      NCCL_TRY(g_nccl.Recv(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
-                           root->stream));
+                             cudaMemcpyDeviceToDevice, ss[0]));
+  if (b->shards.size() > 1) {
+    std::lock_guard<std::mutex> lk(g_nccl.mu);
+    TRY(nccl_comms(b->shards));
+    NCCL_TRY(g_nccl.GroupStart());
+    for (size_t i = 1; i < b->shards.size(); i++) {
+      const Shard& sh = b->shards[i];
+      uint32_t* at_root = d_flat + sh.begin * W;
+      if (scatter) {
+        NCCL_TRY(g_nccl.Send(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
+                             ss[0]));
+        NCCL_TRY(g_nccl.Recv(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i], ss[i]));
+      } else {
+        NCCL_TRY(g_nccl.Send(b->d[i], sh.count * W, kNcclUint32, 0, g_nccl.comms[i], ss[i]));
+        NCCL_TRY(g_nccl.Recv(at_root, sh.count * W, kNcclUint32, (int)i, g_nccl.comms[0],
+                             ss[0]));
+      }
     }
+    NCCL_TRY(g_nccl.GroupEnd());
   }
-  NCCL_TRY(g_nccl.GroupEnd());
+  for (size_t i = 0; i < b->shards.size(); i++) {
+    CUDA_TRY(cudaSetDevice(b->shards[i].dev->id));
+    TRY(batch_touch({b}, i, ss[i]));
+  }
   return 0;
 }
 
@@ -2152,11 +2225,14 @@ int ipclb200_encrypt_batch(const ipclb200_pubkey* pk, const ipclb200_batch* pt,
     const Shard& sh = ct->shards[i];
     if (sh.count == 0) continue;
     Op op;
-    TRY(op.open_on(sh.dev, sh.dev->stream));
+    cudaStream_t bs = nullptr;
+    TRY(batch_stream({pt, make_secure ? r : nullptr, ct}, i, sh.dev, &bs));
+    TRY(op.open_on(sh.dev, bs));
     TRY(encrypt_dev_impl(op, pk, pt->d[i], pt->words, make_secure ? r->d[i] : nullptr,
                          make_secure ? r->words : 0,
                          make_secure ? (r_bits > 0 ? r_bits : r->words * 32) : 0, sh.count,
                          make_secure, ct->d[i]));
+    TRY(batch_touch({pt, make_secure ? r : nullptr, ct}, i, bs));
   }
   return 0;
 }
@@ -2176,8 +2252,11 @@ int ipclb200_decrypt_batch(const ipclb200_privkey* sk, const ipclb200_batch* ct,
     const Shard& sh = ct->shards[i];
     if (sh.count == 0) continue;
     Op op;
-    TRY(op.open_on(sh.dev, sh.dev->stream));
+    cudaStream_t bs = nullptr;
+    TRY(batch_stream({ct, pt}, i, sh.dev, &bs));
+    TRY(op.open_on(sh.dev, bs));
     TRY(decrypt_dev_impl(op, sk, ct->d[i], sh.count, use_crt, pt->d[i]));
+    TRY(batch_touch({ct, pt}, i, bs));
   }
   return 0;
 }
@@ -2200,7 +2279,9 @@ int ipclb200_modmul_batch(const ipclb200_batch* a, const ipclb200_batch* b,
     const Shard& sh = out->shards[i];
     if (sh.count == 0) continue;
     Op op;
-    TRY(op.open_on(sh.dev, sh.dev->stream));
+    cudaStream_t bs = nullptr;
+    TRY(batch_stream({a, b, out}, i, sh.dev, &bs));
+    TRY(op.open_on(sh.dev, bs));
     const uint32_t* d_b = b ? b->d[i] : nullptr;
     if (!b) {
       uint32_t* t;
@@ -2211,6 +2292,7 @@ int ipclb200_modmul_batch(const ipclb200_batch* a, const ipclb200_batch* b,
     }
     TRY(modmul_on(op, a->d[i], d_b, n, mod_words, sh.count, b ? 0u : IPCLB200_SHARED_B,
                   out->d[i]));
+    TRY(batch_touch({a, b, out}, i, bs));
   }
   return 0;
 }
@@ -2241,7 +2323,9 @@ int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
     const Shard& sh = out->shards[i];
     if (sh.count == 0) continue;
     Op op;
-    TRY(op.open_on(sh.dev, sh.dev->stream));
+    cudaStream_t bs = nullptr;
+    TRY(batch_stream({base, exp, out}, i, sh.dev, &bs));
+    TRY(op.open_on(sh.dev, bs));
     const uint32_t* d_exp = exp ? exp->d[i] : nullptr;
     const uint8_t* d_sched = nullptr;
     if (!exp) {
@@ -2260,6 +2344,7 @@ int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
     TRY(modexp_shared_dev(op, base->d[i], d_exp, n, mod_words, exp_words, exp_bits, sh.count,
                           IPCLB200_SHARED_MOD | (exp ? 0u : IPCLB200_SHARED_EXP), d_sched,
                           out->d[i]));
+    TRY(batch_touch({base, exp, out}, i, bs));
     if (!exp) CUDA_TRY(cudaStreamSynchronize(op.s));  // pageable staging of sched / h_exp
   }
   return 0;

@@ -63,6 +63,10 @@ TEST(DeviceResidentTest, ChainStaysInHBM) {
     BigNumber want = ((f.a[i] + f.b[i]) * f.k[i] + f.a[i]) % n;
     EXPECT_EQ(dt.getElement(i), want);
   }
+  // single-element reads come from the flat host image: ONE download, no
+  // vector<BigNumber> for the whole batch
+  EXPECT_TRUE(!dt.isHostMaterialized());
+  EXPECT_EQ(dt.getTexts().size(), f.a.size());
   EXPECT_TRUE(dt.isHostMaterialized());
   // the intermediate values are still readable afterwards and are valid
   // ciphertexts of what they should be
