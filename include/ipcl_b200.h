@@ -162,6 +162,16 @@ typedef struct ipclb200_privkey ipclb200_privkey;
 int ipclb200_privkey_create(const uint32_t* p, const uint32_t* q, int p_words,
                             ipclb200_privkey** out);
 void ipclb200_privkey_destroy(ipclb200_privkey* sk);
+/* Schedule of the key's SECRET exponents (p-1, q-1 in decryptCRT, lambda in
+ * decryptRAW).  constant_schedule != 0: fixed-window ladders whose sequence of
+ * squarings and multiplies depends on the exponent's bit length only -- the
+ * property of the reference's mbx_exp_mb8 -- at ~8 % more products;
+ * 0: host-built sliding-window schedules (the default, fastest; the operation
+ * sequence is the same for every ciphertext but is derived from the key).
+ * Table indices are exponent-dependent addresses in both modes.  Keys whose
+ * primes do not fill their words use the full-width CRT kernel, which only has
+ * the sliding-window form.  Default for new keys: IPCLB200_CONSTANT_SCHEDULE. */
+int ipclb200_privkey_set_schedule(ipclb200_privkey* sk, int constant_schedule);
 
 /* pt[i] = Dec(ct[i]).  use_crt != 0: PrivateKey::decryptCRT,
  * ipcl/pri_key.cpp:114-152; use_crt == 0: decryptRAW, :92-111.

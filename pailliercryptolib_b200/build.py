@@ -143,7 +143,8 @@ def build_cpp_tests(force=False):
             ("main.cpp", "test_cryptography.cpp", "test_ops.cpp",
              "test_serialization.cpp", "test_device_resident.cpp")]
     deps = srcs + [os.path.join(CPP_TEST_DIR, "check.hpp"),
-                   os.path.join(CPP_TEST_DIR, "iso_vectors.hpp"), IPCL_LIB]
+                   os.path.join(CPP_TEST_DIR, "iso_vectors.hpp"),
+                   os.path.join(CPP_TEST_DIR, "serial_golden.hpp"), IPCL_LIB]
     if force or not _newer(CPP_TEST_BIN, deps):
         _run(["g++", "-O2", "-std=c++17", "-fopenmp"] + inc + ["-o", CPP_TEST_BIN]
              + srcs + ["-L", LIBDIR, "-lipcl", "-lipcl_b200",

@@ -43,7 +43,7 @@ EXPORTS = [
     "ipclb200_batch_sync", "ipclb200_batch_scatter", "ipclb200_batch_gather",
     "ipclb200_encrypt_batch", "ipclb200_decrypt_batch", "ipclb200_modmul_batch",
     "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
-    "ipclb200_batch_touch",
+    "ipclb200_batch_touch", "ipclb200_privkey_set_schedule",
 ]
 
 
@@ -242,6 +242,10 @@ class PrivKey:
                                            ctypes.c_size_t(ct.shape[0]), _p(x),
                                            ctypes.byref(xw)))
         return x
+
+    def set_schedule(self, constant):
+        """constant-schedule (fixed-window) ladders for the secret exponents"""
+        _check(lib().ipclb200_privkey_set_schedule(self._h, int(bool(constant))))
 
     def decrypt_batch(self, ct, pt, use_crt=True):
         _check(lib().ipclb200_decrypt_batch(self._h, ct._h, int(use_crt), pt._h))

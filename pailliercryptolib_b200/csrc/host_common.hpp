@@ -180,6 +180,30 @@ inline std::vector<uint32_t> hensel_schedule(const std::vector<uint8_t>& sched) 
   return out;
 }
 
+// The constant schedule of decrypt_hensel_kernel for a SECRET exponent: fixed
+// 4-bit windows over a table of all 16 powers -- every window is four squarings
+// and one multiply whatever the exponent's bits are, so the sequence of
+// operations (and the run time) depends on the bit length only.  The table
+// index of each multiply is still an exponent-dependent address.
+inline std::vector<uint32_t> hensel_schedule_fixed(const Limbs& e) {
+  const int w = 4;
+  const int bits = hbn::bitlen(e);
+  const int nwin = (bits + w - 1) / w;
+  auto window = [&](int k) {
+    uint32_t v = 0;
+    for (int b = w - 1; b >= 0; b--) {
+      const int i = k * w + b;
+      const uint32_t bit = (i < bits) ? ((e[(size_t)i / 32] >> (i % 32)) & 1u) : 0u;
+      v = (v << 1) | bit;
+    }
+    return v;
+  };
+  std::vector<uint32_t> out = {16u | (1u << 8), window(nwin - 1)};
+  for (int k = nwin - 2; k >= 0; k--) out.push_back(((uint32_t)w << 8) | window(k));
+  out.push_back(0xffu);
+  return out;
+}
+
 // per-side constants of the two-digit decrypt (10*pl words):
 //   p | pairs (k0_j, kw_j) of R^(j+1) mod p^2 in Montgomery form, j = 0..3 | -hp mod p
 // A pair (x0, w) stands for x0 - w*p mod p^2 (mont_hensel.cuh).

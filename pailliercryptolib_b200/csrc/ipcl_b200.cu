@@ -279,20 +279,45 @@ struct Op {
 // device, never returned: threads are few).  Batches carry an event, so work
 // of different threads on different batches overlaps while every batch sees its
 // own operations in order.
+struct ThreadStreams {
+  cudaStream_t s[kMaxDevices] = {};
+  Dev* owner[kMaxDevices] = {};
+  ~ThreadStreams();
+};
+
 cudaStream_t thread_stream(Dev* d) {
-  thread_local cudaStream_t streams[kMaxDevices] = {};
-  thread_local Dev* owners[kMaxDevices] = {};
-  if (owners[d->id] != d || !streams[d->id]) {
+  thread_local ThreadStreams ts;
+  if (ts.owner[d->id] != d || !ts.s[d->id]) {
     cudaSetDevice(d->id);
     cudaStream_t s = nullptr;
-    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+    {
+      // streams of threads that have ended wait in the device's pool (with the
+      // pool memory the allocator associates with them)
+      std::lock_guard<std::mutex> lk(d->mu);
+      if (!d->idle.empty()) {
+        s = d->idle.back();
+        d->idle.pop_back();
+      }
+    }
+    if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
       cudaGetLastError();
       return d->stream;
     }
-    streams[d->id] = s;
-    owners[d->id] = d;
+    ts.s[d->id] = s;
+    ts.owner[d->id] = d;
   }
-  return streams[d->id];
+  return ts.s[d->id];
+}
+
+ThreadStreams::~ThreadStreams() {
+  for (int i = 0; i < kMaxDevices; i++) {
+    if (!s[i]) continue;
+    Dev* d = g.dev[i].load();
+    if (d && d == owner[i]) {  // not after ipclb200_shutdown()
+      std::lock_guard<std::mutex> lk(d->mu);
+      d->idle.push_back(s[i]);
+    }
+  }
 }
 
 // restores the caller's current device when a multi-device call returns
@@ -573,8 +598,10 @@ struct ipclb200_privkey {
   std::vector<uint32_t> h_const;  // p q pm1 qm1 hpR hqR pinvR | n muR | n0inv | lambda
   std::vector<uint8_t> h_sched;   // schedules of p-1, q-1, [experiments], lambda
   size_t off_sched_q = 0, off_prog_p = 0, off_prog_q = 0, off_sched_lambda = 0;
-  std::vector<uint32_t> h_hensel;  // 10*pl per side, then the two run schedules
-  size_t off_hsched_p = 0, off_hsched_q = 0;
+  std::vector<uint32_t> h_hensel;  // 10*pl per side, then the run schedules
+  size_t off_hsched_p = 0, off_hsched_q = 0;        // sliding window
+  size_t off_hfixed_p = 0, off_hfixed_q = 0;        // constant schedule
+  std::atomic<int> constant_schedule{0};            // ipclb200_privkey_set_schedule
   bool hensel_ok = false;
   uint32_t p_inv32 = 0, q_inv32 = 0, p_n0inv = 0, q_n0inv = 0, n_inv32 = 0, n_n0inv = 0;
   int pm1_bits = 0, qm1_bits = 0, lambda_bits = 0;
@@ -1045,6 +1072,21 @@ PrivPtrs priv_ptrs(const ipclb200_privkey* sk, const PrivDev* sd) {
   return r;
 }
 
+// Schedule of the secret exponents (p-1, q-1, lambda) of a private key:
+// ipclb200_privkey_set_schedule, default from IPCLB200_CONSTANT_SCHEDULE (0).
+// Constant: every kernel runs a fixed-window ladder whose operation sequence
+// depends on the exponent's bit length only (as mbx_exp_mb8 does); otherwise
+// the host-built sliding-window schedule (about 8 % fewer products).
+bool secret_schedule_is_constant(const ipclb200_privkey* sk) {
+  const int v = sk->constant_schedule.load();
+  if (v == 1) return true;
+  if (v == 2) return false;
+  const char* e = getenv("IPCLB200_CONSTANT_SCHEDULE");
+  if (e && e[0] == '1') return true;
+  const char* ns = getenv("IPCLB200_NO_SCHED");
+  return ns && ns[0] == '1';
+}
+
 // CRT decrypt in two-digit arithmetic (decrypt_hensel_kernel + crt_combine_kernel)
 int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
                         const uint32_t* d_ct, size_t count, uint32_t* d_pt) {
@@ -1055,10 +1097,12 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
   DecryptHenselParams p{};
   p.ct = d_ct;
   p.s0.blk = sd->d_hensel;
-  p.s0.sched = sd->d_hensel + sk->off_hsched_p;
+  // secret exponents p-1, q-1: sliding window (fastest) or the constant schedule
+  const bool fixed = secret_schedule_is_constant(sk);
+  p.s0.sched = sd->d_hensel + (fixed ? sk->off_hfixed_p : sk->off_hsched_p);
   p.s0.n0inv = sk->p_n0inv;
   p.s1.blk = sd->d_hensel + 10 * (size_t)pl;
-  p.s1.sched = sd->d_hensel + sk->off_hsched_q;
+  p.s1.sched = sd->d_hensel + (fixed ? sk->off_hfixed_q : sk->off_hsched_q);
   p.s1.n0inv = sk->q_n0inv;
   p.mpq = d_mpq;
   p.count = count;
@@ -1244,10 +1288,7 @@ int decrypt_dev_impl(Op& op, const ipclb200_privkey* sk, const uint32_t* d_ct, s
     p.n0_stride = 0;
     p.out = d_x;
     p.count = count;
-    {
-      const char* ns = getenv("IPCLB200_NO_SCHED");
-      if (!(ns && ns[0] == '1')) p.sched = pp.sched_lambda;
-    }
+    if (!secret_schedule_is_constant(sk)) p.sched = pp.sched_lambda;
     TRY(launch_modexp(op, p, L));
     RawFinishParams f{};
     f.x = d_x;
@@ -1833,13 +1874,19 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in, int p_wo
                     (pl == 16 || pl == 32 || pl == 48 || pl == 64);
     if (sk->hensel_ok) {
       std::vector<uint32_t> hs_p = hensel_schedule(sp), hs_q = hensel_schedule(sq);
-      sk->h_hensel.assign(20 * (size_t)pl + hs_p.size() + hs_q.size(), 0u);
+      std::vector<uint32_t> hf_p = hensel_schedule_fixed(pm1), hf_q = hensel_schedule_fixed(qm1);
+      sk->h_hensel.assign(20 * (size_t)pl + hs_p.size() + hs_q.size() + hf_p.size() +
+                              hf_q.size(), 0u);
       hensel_side_block(p, psq, hp, pl, sk->h_hensel.data());
       hensel_side_block(q, qsq, hq, pl, sk->h_hensel.data() + 10 * (size_t)pl);
       sk->off_hsched_p = 20 * (size_t)pl;
       sk->off_hsched_q = sk->off_hsched_p + hs_p.size();
+      sk->off_hfixed_p = sk->off_hsched_q + hs_q.size();
+      sk->off_hfixed_q = sk->off_hfixed_p + hf_p.size();
       std::copy(hs_p.begin(), hs_p.end(), sk->h_hensel.begin() + sk->off_hsched_p);
       std::copy(hs_q.begin(), hs_q.end(), sk->h_hensel.begin() + sk->off_hsched_q);
+      std::copy(hf_p.begin(), hf_p.end(), sk->h_hensel.begin() + sk->off_hfixed_p);
+      std::copy(hf_q.begin(), hf_q.end(), sk->h_hensel.begin() + sk->off_hfixed_q);
     }
   }
 #ifdef IPCLB200_EXPERIMENTS
@@ -1850,6 +1897,12 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in, int p_wo
   PrivDev* sd = nullptr;
   TRY(priv_dev(sk.get(), dev, &sd));
   *out = sk.release();
+  return 0;
+}
+
+int ipclb200_privkey_set_schedule(ipclb200_privkey* sk, int constant_schedule) {
+  if (!sk) return fail(IPCLB200_ERR_BAD_ARG, "set_schedule: null key");
+  sk->constant_schedule.store(constant_schedule ? 1 : 2);
   return 0;
 }
 

@@ -560,7 +560,8 @@ __global__ void __launch_bounds__(kBlockThreads, DECRYPT_MIN_BLOCKS)
 // --------------------------------------------------------------------------
 struct HenselSide {
   const uint32_t* blk;   // p | (k0_j | kw_j), j = 0..3 | -hp mod p    (10*LH words)
-  const uint32_t* sched; // [nodd, first, (run << 8 | entry)..., (run << 8 | 0xff)]
+  // [entries | all_powers << 8, first, (run << 8 | entry)..., (run << 8 | 0xff)]
+  const uint32_t* sched;
   uint32_t n0inv;
 };
 
@@ -641,25 +642,57 @@ __global__ void __launch_bounds__(kBlockThreads, MINB)
         }
       }
     }
-    // ---- odd powers x, x^3, ..., into the workspace slot ------------------------
-    const int nodd = (int)__ldg(sched);
-    M::store(tab, x0);
-    M::store(tab + LH, w);
-    if (nodd > 1) {
-      // x^2 into the table-entry buffer, then x^(2i+1) = x^(2i-1) * x^2
+    // ---- the table in the workspace slot: odd powers x, x^3, ... (sliding
+    // window) or, for the constant schedule, all powers x^0 .. x^(n-1) -----------
+    const uint32_t tab_word = __ldg(sched);
+    const int nodd = (int)(tab_word & 0xffu);
+    const bool all_powers = (tab_word >> 8) != 0;
+    if (all_powers) {
+      // x^0 = 1 in Montgomery form: R mod p^2 = (R - p) + 1*p, i.e. the pair
+      // (R - p, p - 1); p is odd, so neither +1 nor -1 carries
+      uint32_t o0[K], o1[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        o0[j] = ~n[j];
+        o1[j] = n[j];
+      }
+      if (M::lane_t() == 0) {
+        o0[0] += 1u;
+        o1[0] -= 1u;
+      }
+      M::store(tab, o0);
+      M::store(tab + LH, o1);
+      M::store(tab + 2 * LH, x0);
+      M::store(tab + 3 * LH, w);
+      __syncwarp();
+      H::put(sm + H::kT0, x0);
+      H::put(sm + H::kT0 + LH, w);
+      __syncwarp();
 #pragma unroll 1
-      for (int i = 0; i < nodd; i++) {
-        H::step(x0, w, i != 0, sm + H::kT0, sm, n, n0inv);
-        if (i == 0) {
-          __syncwarp();
-          H::put(sm + H::kT0, x0);
-          H::put(sm + H::kT0 + LH, w);
-          __syncwarp();
-          M::load(x0, tab);
-          M::load(w, tab + LH);
-        } else {
-          M::store(tab + (size_t)i * 2 * LH, x0);
-          M::store(tab + (size_t)i * 2 * LH + LH, w);
+      for (int i = 2; i < nodd; i++) {
+        H::step(x0, w, true, sm + H::kT0, sm, n, n0inv);  // x^i = x^(i-1) * x
+        M::store(tab + (size_t)i * 2 * LH, x0);
+        M::store(tab + (size_t)i * 2 * LH + LH, w);
+      }
+    } else {
+      M::store(tab, x0);
+      M::store(tab + LH, w);
+      if (nodd > 1) {
+        // x^2 into the table-entry buffer, then x^(2i+1) = x^(2i-1) * x^2
+#pragma unroll 1
+        for (int i = 0; i < nodd; i++) {
+          H::step(x0, w, i != 0, sm + H::kT0, sm, n, n0inv);
+          if (i == 0) {
+            __syncwarp();
+            H::put(sm + H::kT0, x0);
+            H::put(sm + H::kT0 + LH, w);
+            __syncwarp();
+            M::load(x0, tab);
+            M::load(w, tab + LH);
+          } else {
+            M::store(tab + (size_t)i * 2 * LH, x0);
+            M::store(tab + (size_t)i * 2 * LH + LH, w);
+          }
         }
       }
     }

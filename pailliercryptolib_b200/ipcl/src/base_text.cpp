@@ -5,6 +5,7 @@
 #include "ipcl/base_text.hpp"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
 #include <utility>
@@ -135,14 +136,22 @@ bool deviceResidentEnabled() {
 // lazy host materialisation happens inside const accessors that several
 // threads may call on one text; one process-wide lock is enough (it is taken
 // once per text)
-static std::mutex g_materialize_mutex;
+// Lazy host materialisation happens inside const accessors that several
+// threads may call on one text.  The lock is held while a download completes,
+// so it must not be shared between unrelated texts (four callers working on
+// their own batches would queue on it): one of 64 locks chosen by the text's
+// address.
+static std::mutex& lockFor(const void* text) {
+  static std::mutex locks[64];
+  return locks[(reinterpret_cast<std::uintptr_t>(text) >> 6) & 63];
+}
 
 BaseText::BaseText(std::shared_ptr<detail::DeviceBatch> dev)
     : m_size(dev->count), m_dev(std::move(dev)), m_host_valid(false) {}
 
 void BaseText::ensureHost() const {
   if (m_host_valid.load(std::memory_order_acquire)) return;
-  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  std::lock_guard<std::mutex> lk(lockFor(this));
   if (m_host_valid.load(std::memory_order_relaxed)) return;
   if (m_flat)
     m_texts = detail::unpack(m_flat->slab.p, m_flat->count, m_flat->words);
@@ -154,7 +163,7 @@ void BaseText::ensureHost() const {
 // the flat host image of a device-resident text: ONE download, no BigNumber
 // objects; single-element accessors read from it
 const detail::FlatImage* BaseText::flatImage() const {
-  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  std::lock_guard<std::mutex> lk(lockFor(this));
   if (!m_flat && m_dev) {
     auto img = std::make_shared<detail::FlatImage>(m_dev->count, m_dev->words);
     m_dev->downloadFlat(img->slab.p);
@@ -177,7 +186,7 @@ void BaseText::hostOnly() {
 }
 
 std::shared_ptr<detail::DeviceBatch> BaseText::deviceBatch(int words) const {
-  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  std::lock_guard<std::mutex> lk(lockFor(this));
   if (m_dev && m_dev->words == words) return m_dev;
   if (!m_host_valid.load()) {
     // resident at another width: go through the host form
@@ -217,7 +226,7 @@ BaseText::BaseText(std::vector<BigNumber>&& bn_v)
 // a copy shares the (immutable) device batch and copies the host form only if
 // it exists
 BaseText::BaseText(const BaseText& bt) : m_size(bt.m_size) {
-  std::lock_guard<std::mutex> lk(g_materialize_mutex);
+  std::lock_guard<std::mutex> lk(lockFor(&bt));
   m_dev = bt.m_dev;
   m_flat = bt.m_flat;
   const bool valid = bt.m_host_valid.load();
@@ -227,7 +236,14 @@ BaseText::BaseText(const BaseText& bt) : m_size(bt.m_size) {
 
 BaseText& BaseText::operator=(const BaseText& other) {
   if (this != &other) {
-    std::lock_guard<std::mutex> lk(g_materialize_mutex);
+    // both texts: the source may be materialising, the target may be read
+    std::mutex &ma = lockFor(this), &mb = lockFor(&other);
+    std::unique_lock<std::mutex> la(ma, std::defer_lock), lb(mb, std::defer_lock);
+    if (&ma == &mb) {
+      la.lock();
+    } else {
+      std::lock(la, lb);
+    }
     m_size = other.m_size;
     m_dev = other.m_dev;
     m_flat = other.m_flat;

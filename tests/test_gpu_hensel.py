@@ -141,3 +141,26 @@ def test_3072_bit_key_4096_elements_vs_oracle(capi, oracle, keys):
     got = sk.decrypt(ct)
     assert np.array_equal(got, pt)
     assert np.array_equal(got, oracle.decrypt_crt(to_limbs(p, 48), to_limbs(q, 48), ct))
+
+
+@pytest.mark.parametrize("name", ["1024", "2048", "3072", "4096", "2048_low"])
+def test_constant_schedule_mode(capi, all_keys, name, monkeypatch):
+    """ipclb200_privkey_set_schedule(1): fixed 4-bit windows over a table of all 16
+    powers (the operation sequence no longer depends on the bits of p-1, q-1,
+    lambda); same plaintexts as the sliding-window schedules, CRT and RAW"""
+    k = all_keys[name]
+    p, q = sorted((k["p"], k["q"]))
+    pl = (p.bit_length() + 31) // 32
+    rng = np.random.default_rng(len(name) + pl)
+    cts, words = _ciphertexts(rng, p, q, 150)
+    ct = batch_to_limbs(cts, words)
+    sk = capi.PrivKey(to_limbs(p, pl), to_limbs(q, pl))
+    monkeypatch.delenv("IPCLB200_DECRYPT", raising=False)
+    base = sk.decrypt(ct)
+    base_raw = sk.decrypt(ct[:40], use_crt=False)
+    sk.set_schedule(True)
+    assert np.array_equal(sk.decrypt(ct), base)
+    assert np.array_equal(sk.decrypt(ct[:40], use_crt=False), base_raw)
+    sk.set_schedule(False)
+    assert np.array_equal(sk.decrypt(ct), base)
+    assert batch_from_limbs(base[:6]) == [dec_crt(p, q, c) for c in cts[:6]]
