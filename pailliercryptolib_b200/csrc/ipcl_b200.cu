@@ -502,6 +502,7 @@ struct CombTable {
   uint32_t* d = nullptr;
   int w = 0, windows = 0;
   bool full = false;  // built at the budget width
+  bool pairs = false;  // entries are two-digit pairs (encrypt_hensel_kernel)
   size_t bytes = 0;
   cudaEvent_t ready = nullptr;  // recorded behind the build kernels
 };
@@ -513,6 +514,7 @@ struct PubDev {
   std::shared_ptr<DevModulus> msq;
   uint32_t* d_const = nullptr;  // [nR (L) | hs_m (L) | n as exponent (nl)]
   uint8_t* d_sched_n = nullptr;
+  uint32_t* d_hensel = nullptr;  // n | R^2 mod n | conversion pairs (hensel_ok keys)
   CombTable cur, next;
   bool next_pending = false;
   std::vector<CombTable> retired;  // replaced tables, freed with the key
@@ -567,6 +569,12 @@ struct ipclb200_pubkey {
   int rand_bits = 0;
   std::vector<uint32_t> h_const;
   std::vector<uint8_t> h_sched_n;
+  // two-digit encrypt (mont_hensel.cuh, digits base n): n | R^2 mod n | the pairs
+  // of 1, R (Montgomery windows) | the pairs of R^-1, 1 (plain window 0);
+  // hensel_ok: n fills its nl words and nl is a layout of encrypt_hensel_kernel
+  std::vector<uint32_t> h_hensel;
+  bool hensel_ok = false;
+  uint32_t n_n0inv = 0;
   // fixed-base table policy (ipclb200_pubkey_set_table_policy)
   size_t comb_max_mb = 4096;
   size_t comb_upgrade_at = 8192;
@@ -581,6 +589,7 @@ struct ipclb200_pubkey {
       cudaDeviceSynchronize();
       if (pd->d_const) cudaFree(pd->d_const);
       if (pd->d_sched_n) cudaFree(pd->d_sched_n);
+      if (pd->d_hensel) cudaFree(pd->d_hensel);
       free_comb(live, pd->cur);
       free_comb(live, pd->next);
       for (auto& t : pd->retired) free_comb(live, t);
@@ -647,6 +656,11 @@ int pub_dev(const ipclb200_pubkey* pk_c, Dev* dev, PubDev** out) {
     CUDA_TRY(cudaMalloc(&pd->d_const, pk->h_const.size() * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpy(pd->d_const, pk->h_const.data(),
                         pk->h_const.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (pk->hensel_ok) {
+      CUDA_TRY(cudaMalloc(&pd->d_hensel, pk->h_hensel.size() * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemcpy(pd->d_hensel, pk->h_hensel.data(),
+                          pk->h_hensel.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     if (!pk->h_sched_n.empty()) {
       CUDA_TRY(cudaMalloc(&pd->d_sched_n, pk->h_sched_n.size()));
       CUDA_TRY(cudaMemcpy(pd->d_sched_n, pk->h_sched_n.data(), pk->h_sched_n.size(),
@@ -855,20 +869,34 @@ int build_comb(const ipclb200_pubkey* pk, PubDev* pd, int bits, bool small, cuda
     if (v >= 1 && v <= 16) w = v;
   }
   CombTable t;
+  // the wide table of a key whose n fills its words is stored as two-digit pairs
+  // (encrypt_hensel_kernel: 5/8 of the multiplies per window); it is built in
+  // full-width form first (a stream-ordered temporary) and converted
+  const char* no_h = getenv("IPCLB200_NO_HENSEL_ENCRYPT");
+  const bool pairs = !small && pk->hensel_ok && !(no_h && no_h[0] == '1');
+  uint32_t* d_full = nullptr;
   // back off to narrower windows if the allocation does not fit
   for (;; w--) {
     cudaError_t e = cudaMalloc(&t.d, comb_table_words(L, bits, w) * sizeof(uint32_t));
+    if (e == cudaSuccess && pairs) {
+      e = cudaMallocAsync(&d_full, comb_table_words(L, bits, w) * sizeof(uint32_t), s);
+      if (e != cudaSuccess) {
+        cudaFree(t.d);
+        t.d = nullptr;
+      }
+    }
     if (e == cudaSuccess) break;
     cudaGetLastError();
     t.d = nullptr;
     if (w <= 4) return fail(IPCLB200_ERR_CUDA, "cannot allocate the fixed-base table");
   }
+  uint32_t* d_build = pairs ? d_full : t.d;
   int windows = (bits + w - 1) / w;
   if (windows < 1) windows = 1;
   CombParams cp{};
   cp.m = pd->msq->mc;
   cp.hs_m = pd->d_const + L;
-  cp.comb = t.d;
+  cp.comb = d_build;
   cp.w = w;
   cp.w_lo = w > 11 ? (w + 1) / 2 : w;  // two-level build for wide windows
   cp.windows = windows;
@@ -891,6 +919,45 @@ int build_comb(const ipclb200_pubkey* pk, PubDev* pd, int bits, bool small, cuda
 #undef F
   g.launches += 2;
   CUDA_TRY(cudaGetLastError());
+  if (pairs) {
+    const int nl = pk->nl;
+    CombPairsParams cv{};
+    cv.in = d_full;
+    cv.out = t.d;
+    cv.count = (size_t)windows << w;
+    cv.plain_entries = (size_t)1 << w;
+    cv.blk = pd->d_hensel;
+    cv.consts_mont = pd->d_hensel + 2 * (size_t)nl;
+    cv.consts_plain = pd->d_hensel + 6 * (size_t)nl;
+    cv.n0inv = pk->n_n0inv;
+    uint32_t* cnt = nullptr;
+    CUDA_TRY(cudaMallocAsync(&cnt, 16, s));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, s));
+    cv.work_counter = reinterpret_cast<unsigned int*>(cnt);
+#define FP(K_, T_)                                                                       \
+  {                                                                                      \
+    auto kern = comb_pairs_kernel<K_, T_>;                                               \
+    const size_t smem = (size_t)(kBlockThreads / T_) * HMont<K_, T_, 4>::kStride * 4;    \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                           \
+    int grid = 0;                                                                        \
+    TRY(grid_for(pd->dev, kern, cv.count, T_, smem, &grid));                             \
+    kern<<<grid, kBlockThreads, smem, s>>>(cv);                                          \
+  }
+    switch (nl) {
+      case 32: FP(16, 2) break;
+      case 64: FP(16, 4) break;
+      case 96: FP(12, 8) break;
+      case 128: FP(16, 8) break;
+      default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel encrypt: unsupported key width");
+    }
+#undef FP
+    g.launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(cnt, s));
+    CUDA_TRY(cudaFreeAsync(d_full, s));
+    t.pairs = true;
+  }
   CUDA_TRY(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(t.ready, s));
   t.w = w;
@@ -978,6 +1045,49 @@ int comb_for_launch(const ipclb200_pubkey* pk_c, PubDev* pd, int bits, size_t co
   return 0;
 }
 
+// DJN encrypt in two-digit arithmetic from a table of pairs (K3h)
+int encrypt_hensel_launch(Op& op, const ipclb200_pubkey* pk, PubDev* pd,
+                          const EncryptParams& e) {
+  const int nl = pk->nl;
+  EncryptHenselParams p{};
+  p.pt = e.pt;
+  p.pt_words = e.pt_words;
+  p.r = e.r;
+  p.r_words = e.r_words;
+  p.blk = pd->d_hensel;
+  p.n0inv = pk->n_n0inv;
+  p.comb = e.comb;
+  p.comb_w = e.comb_w;
+  p.comb_windows = e.comb_windows;
+  p.ct = e.ct;
+  p.count = e.count;
+  {
+    uint32_t* ws = nullptr;
+    TRY(table_ws(op, 0, &ws, &p.work_counter));
+  }
+#define FE(K_, T_, MINB_)                                                                \
+  {                                                                                      \
+    auto kern = encrypt_hensel_kernel<K_, T_, MINB_, 8>;                                 \
+    constexpr size_t smem = encrypt_hensel_smem_bytes<K_, T_>(kBlockThreads);            \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                           \
+    int grid = 0;                                                                        \
+    TRY(grid_for(op.dev, kern, e.count, T_, smem, &grid));                               \
+    kern<<<grid, kBlockThreads, smem, op.s>>>(p);                                        \
+  }
+  switch (nl) {
+    case 32: FE(16, 2, 3) break;
+    case 64: FE(16, 4, 3) break;
+    case 96: FE(12, 8, 3) break;
+    case 128: FE(16, 8, 3) break;
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel encrypt: unsupported key width");
+  }
+#undef FE
+  g.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int encrypt_dev_impl(Op& op, const ipclb200_pubkey* pk, const uint32_t* d_pt, int pt_words,
                      const uint32_t* d_r, int r_words, int r_bits, size_t count,
                      int make_secure, uint32_t* d_ct) {
@@ -1013,6 +1123,7 @@ int encrypt_dev_impl(Op& op, const ipclb200_pubkey* pk, const uint32_t* d_pt, in
       p.comb_w = t.w;
       p.comb_windows = (r_bits + t.w - 1) / t.w;
       if (p.comb_windows < 1) p.comb_windows = 1;
+      if (t.pairs) return encrypt_hensel_launch(op, pk, pd, p);
     } else {
       p.mode = 2;
       p.window = pick_window(r_bits);
@@ -1681,6 +1792,33 @@ int ipclb200_pubkey_create(const uint32_t* n, int n_words, const uint32_t* hs, i
   } else {
     // non-DJN obfuscator r^n: every element has the exponent n
     pk->h_sched_n = build_schedule(pk->n, kSchedWindow);
+  }
+  pk->n_n0inv = hbn::neg_inv32(pk->n[0]);
+  pk->hensel_ok = pk->djn && hbn::bitlen(pk->n) == 32 * n_words &&
+                  (n_words == 32 || n_words == 64 || n_words == 96 || n_words == 128);
+  if (pk->hensel_ok) {
+    const int nl = n_words;
+    const Limbs Rh = hbn::pow2(32u * (unsigned)nl);
+    pk->h_hensel.assign(10 * (size_t)nl, 0u);
+    uint32_t* hb = pk->h_hensel.data();
+    hbn::to_words(pk->n, hb, nl);
+    hbn::to_words(hbn::mod(hbn::mul(hbn::mod(Rh, pk->n), hbn::mod(Rh, pk->n)), pk->n), hb + nl, nl);
+    // raw pair (x0, w) of an integer t mod n^2: t = x0 - w*n
+    auto raw_pair = [&](const Limbs& t, uint32_t* dst) {
+      Limbs hi, lo;
+      hbn::divmod(hbn::mod(t, pk->nsq), pk->n, &hi, &lo);
+      Limbs wneg = hbn::mod(hi, pk->n);
+      Limbs w = hbn::is_zero(wneg) ? wneg : hbn::sub(pk->n, wneg);
+      hbn::to_words(lo, dst, nl);
+      hbn::to_words(w, dst + nl, nl);
+    };
+    Limbs one = hbn::from_u64(1), rinv;
+    if (!hbn::modinv(hbn::mod(Rh, pk->nsq), pk->nsq, &rinv))
+      return fail(IPCLB200_ERR_BAD_ARG, "pubkey_create: R not invertible mod n^2");
+    raw_pair(one, hb + 2 * (size_t)nl);   // Montgomery windows: chunk 0 * 1
+    raw_pair(Rh, hb + 4 * (size_t)nl);    //                     chunk 1 * R
+    raw_pair(rinv, hb + 6 * (size_t)nl);  // plain window:       chunk 0 * R^-1
+    raw_pair(one, hb + 8 * (size_t)nl);   //                     chunk 1 * 1
   }
   Dev* dev = nullptr;
   TRY(primary_device(&dev));

@@ -618,30 +618,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB)
     M::load(n, blk);
     uint32_t x0[K], w[K];
     // ---- prologue: ct -> (x0, w) = ct * R mod p^2 -----------------------------
-    {
-      const uint32_t* c = p.ct + ii * (size_t)(4 * LH);
-#pragma unroll 1
-      for (int j = 0; j < 4; j++) {
-        uint32_t a[K], z0[K], wz[K];
-        __syncwarp();
-        M::load(a, blk + (size_t)(1 + 2 * j) * LH);
-        H::put(sm + H::kS0, a);
-        M::load(a, blk + (size_t)(2 + 2 * j) * LH);
-        H::put(sm + H::kS1, a);
-        __syncwarp();
-        M::load(a, c + (size_t)j * LH);
-        H::mul_digit(z0, wz, a, sm, n, n0inv);
-        if (j == 0) {
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            x0[k] = z0[k];
-            w[k] = wz[k];
-          }
-        } else {
-          H::add(x0, w, z0, wz, n);
-        }
-      }
-    }
+    H::enter(x0, w, p.ct + ii * (size_t)(4 * LH), 4, blk + LH, sm, n, n0inv);
     // ---- the table in the workspace slot: odd powers x, x^3, ... (sliding
     // window) or, for the constant schedule, all powers x^0 .. x^(n-1) -----------
     const uint32_t tab_word = __ldg(sched);
@@ -753,6 +730,222 @@ __global__ void __launch_bounds__(kBlockThreads, MINB)
       H::pass_a(t, w, sm + H::kS0, sm + H::kSQ, n, n0inv);
       M::sub_n_if_ge(t, n);
       if (valid) M::store(p.mpq + (inst * 2 + side) * LH, t);
+    }
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------------
+// K3h: DJN encrypt in two-digit arithmetic mod n^2 (digits base n, LH = words of
+//     n), mont_hensel.cuh.  obf = hs^r is the product of one fixed-base table
+//     entry per window (K5), entries stored as pairs: 5 half-width limb products
+//     per window instead of 8.  Window 0 is stored in plain form, the others in
+//     Montgomery form, so the running product stays plain: obf = u0 - uw*n.
+//     With a = u0 mod n (u0 = a + c*n):
+//         ct = obf * (1 + m*n) = a + ((c + a*m - uw) mod n) * n      (mod n^2)
+//     -- canonical by construction: one half-width modular product a*m, one
+//     plain LH x LH product t*n.  Entries are fetched into shared memory by TMA
+//     bulk copies, double buffered, one window ahead.
+// --------------------------------------------------------------------------
+struct EncryptHenselParams {
+  const uint32_t* pt;
+  int pt_words;
+  const uint32_t* r;
+  int r_words;
+  const uint32_t* blk;   // n | R^2 mod n            (2*LH words)
+  uint32_t n0inv;
+  const uint32_t* comb;  // [windows][1 << w][2*LH]: pairs
+  int comb_w;
+  int comb_windows;      // windows covering this batch's exponents
+  uint32_t* ct;          // count x 2*LH words
+  size_t count;
+  unsigned int* work_counter;
+};
+
+// group area: the HMont layout (S0 | S1 | SQ | entry buffer 0) + entry buffer 1
+template <int K, int T>
+constexpr size_t encrypt_hensel_smem_bytes(int threads) {
+  return (size_t)(threads / T) * (7 * K * T + 4) * sizeof(uint32_t) +
+         (size_t)(threads / 32) * 2 * sizeof(uint64_t);
+}
+
+template <int K, int T, int MINB, int ROWS>
+__global__ void __launch_bounds__(kBlockThreads, MINB)
+    encrypt_hensel_kernel(const EncryptHenselParams p) {
+  using M = Mont<K, T>;
+  using H = HMont<K, T, ROWS>;
+  constexpr int LH = K * T;
+  constexpr int GW = 32 / T;
+  constexpr int kStride = 7 * LH + 4;
+  constexpr int kBuf = 2 * LH;
+  extern __shared__ __align__(16) uint32_t hensel_smem[];
+  const int gib = threadIdx.x / T;
+  uint32_t* sm = hensel_smem + (size_t)gib * kStride;
+  uint32_t* sS0 = sm + H::kS0;
+  uint32_t* sSQ = sm + H::kSQ;
+  uint32_t* sBuf = sm + H::kT0;  // two entry buffers of 2*LH words
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hensel_smem +
+                                              (size_t)(blockDim.x / T) * kStride) +
+                  2 * (threadIdx.x >> 5);
+  const bool warp_leader = (threadIdx.x & 31) == 0;
+  const bool group_leader = M::lane_t() == 0;
+  if (warp_leader) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase[2] = {0, 0};
+  constexpr uint32_t kEntryBytes = 2 * LH * sizeof(uint32_t);
+  const size_t wstride = (size_t)(2 * LH) << p.comb_w;
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  uint32_t n[K];
+  M::load(n, p.blk);
+  const uint32_t n0inv = p.n0inv;
+  for (;;) {
+    const unsigned int wk = claim_chunk(p.work_counter);
+    if (wk >= nchunks) break;
+    const size_t inst = (size_t)wk * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const uint32_t* e = p.r + ii * (size_t)p.r_words;
+    uint32_t x0[K], w[K];
+    // window 0 (plain form) straight into registers, window 1 on its way
+    {
+      const uint32_t* ent = p.comb + (size_t)exp_window(e, p.r_words, 0, p.comb_w) * kBuf;
+      M::load(x0, ent);
+      M::load(w, ent + LH);
+    }
+    __syncwarp();
+    fence_async_proxy();
+    if (p.comb_windows > 1) {
+      if (warp_leader) mbar_expect_tx(bar, GW * kEntryBytes);
+      __syncwarp();
+      if (group_leader)
+        bulk_g2s(sBuf, p.comb + wstride + (size_t)exp_window(e, p.r_words, 1, p.comb_w) * kBuf,
+                 kEntryBytes, bar);
+    }
+#pragma unroll 1
+    for (int k = 1; k < p.comb_windows; k++) {
+      const int b = (k - 1) & 1;
+      if (k + 1 < p.comb_windows) {
+        // the other buffer was last read by the multiply of window k-1
+        __syncwarp();
+        fence_async_proxy();
+        if (warp_leader) mbar_expect_tx(bar + (b ^ 1), GW * kEntryBytes);
+        __syncwarp();
+        if (group_leader)
+          bulk_g2s(sBuf + (b ^ 1) * kBuf,
+                   p.comb + (size_t)(k + 1) * wstride +
+                       (size_t)exp_window(e, p.r_words, k + 1, p.comb_w) * kBuf,
+                   kEntryBytes, bar + (b ^ 1));
+      }
+      mbar_wait(bar + b, phase[b]);
+      phase[b] ^= 1u;
+      H::mul(x0, w, sBuf + b * kBuf, sm, n, n0inv);
+    }
+    // ---- a = u0 mod n (c = 1 if n was taken off), uw mod n ---------------------
+    const uint32_t c = M::sub_n_if_ge(x0, n);
+    M::sub_n_if_ge(w, n);
+    // ---- am = a * m mod n: two half-width Montgomery products (m, then R^2) ------
+    uint32_t t[K];
+    {
+      uint32_t m[K];
+      load_padded<K, T>(m, p.pt + ii * (size_t)p.pt_words, p.pt_words);
+      __syncwarp();
+      H::put(sS0, m);
+      __syncwarp();
+      H::pass_a(t, x0, sS0, sSQ, n, n0inv);  // a*m/R
+      M::load(m, p.blk + LH);
+      __syncwarp();
+      H::put(sS0, m);
+      __syncwarp();
+      uint32_t t2[K];
+      H::pass_a(t2, t, sS0, sSQ, n, n0inv);  // a*m mod n, < R
+#pragma unroll
+      for (int j = 0; j < K; j++) t[j] = t2[j];
+    }
+    M::sub_n_if_ge(t, n);
+    // ---- t = (am + c - uw) mod n --------------------------------------------------
+    {
+      uint32_t y[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = 0;
+      M::group_add(t, y, c);  // am + c <= n
+      M::sub_n_if_ge(t, n);
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = ~w[j];
+      const uint32_t nb = M::group_add(t, y, 1u);  // t - uw; carry out <=> no borrow
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = nb ? 0u : n[j];
+      M::group_add(t, y, 0u);  // + n after a borrow (the carry out cancels it)
+    }
+    // ---- ct = a + t*n: plain LH x LH product, low half through shared memory -------
+    uint32_t hi[K], lo[K];
+    __syncwarp();
+    H::put(sS0, t);
+    __syncwarp();
+    H::mul_plain(hi, n, sS0, sSQ);
+    __syncwarp();
+    M::load(lo, sSQ);  // this lane's K low limbs (shared memory, generic load)
+    {
+      const uint32_t cy = M::group_add(lo, x0, 0u);
+      uint32_t y[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = 0;
+      M::group_add(hi, y, cy);
+    }
+    if (valid) {
+      M::store(p.ct + inst * (size_t)(2 * LH), lo);
+      M::store(p.ct + inst * (size_t)(2 * LH) + LH, hi);
+    }
+    __syncwarp();
+  }
+}
+
+// K5h: full-width Montgomery table entries -> pairs.  in[i] = v_i * R^2 mod n^2
+// (R = 2^(32 LH), the full-width radix is R^2), 2*LH words, any value < R^2.
+// out[i] = the pair of v_i * R mod n^2 (Montgomery form; windows >= 1) or of v_i
+// (plain; window 0): sum of the two LH-word chunks times the constants
+// R^(j-1) resp. R^(j-2) as raw pairs (HMont::enter).
+struct CombPairsParams {
+  const uint32_t* in;
+  uint32_t* out;
+  size_t count;          // entries
+  size_t plain_entries;  // the first entries (window 0) go to plain form
+  const uint32_t* blk;   // n (LH)
+  const uint32_t* consts_mont;   // 2 pairs
+  const uint32_t* consts_plain;  // 2 pairs
+  uint32_t n0inv;
+  unsigned int* work_counter;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kBlockThreads, 3) comb_pairs_kernel(const CombPairsParams p) {
+  using M = Mont<K, T>;
+  using H = HMont<K, T, 4>;
+  constexpr int LH = K * T;
+  constexpr int GW = 32 / T;
+  extern __shared__ __align__(16) uint32_t hensel_smem[];
+  uint32_t* sm = hensel_smem + (size_t)(threadIdx.x / T) * H::kStride;
+  uint32_t n[K];
+  M::load(n, p.blk);
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  for (;;) {
+    const unsigned int wk = claim_chunk(p.work_counter);
+    if (wk >= nchunks) break;
+    const size_t inst = (size_t)wk * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    // all groups of a warp convert entries of the same kind (plain_entries is a
+    // multiple of the chunk size: a power of two >= 16)
+    const bool plain = ((size_t)wk * GW) < p.plain_entries;
+    uint32_t x0[K], w[K];
+    H::enter(x0, w, p.in + ii * (size_t)(2 * LH), 2, plain ? p.consts_plain : p.consts_mont, sm,
+             n, p.n0inv);
+    if (valid) {
+      M::store(p.out + inst * (size_t)(2 * LH), x0);
+      M::store(p.out + inst * (size_t)(2 * LH) + LH, w);
     }
     __syncwarp();
   }

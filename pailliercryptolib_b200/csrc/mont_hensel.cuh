@@ -417,6 +417,96 @@ struct HMont {
     pass_b<false>(wz, a, a, sm + kS1, sm + kS1, sm + kSQ, n, n0inv, 0u, ovA);
   }
 
+  // ---- one row of a PLAIN product (no reduction): P,Q += a*b, the lowest limb
+  //      leaves the accumulator (lane 0: a finished limb of the product) ---------
+  __device__ __forceinline__ static uint32_t row_plain(uint32_t (&P)[K + 1],
+                                                       uint32_t (&Q)[K + 1],
+                                                       const uint32_t (&a)[K], uint32_t b,
+                                                       uint32_t in_limb, uint32_t& out) {
+    uint32_t t0, t1;
+    add_cc(t0, Q[K], in_limb);
+    addc(t1, 0, 0);
+    add_cc(P[0], P[0], Q[1]);
+#pragma unroll
+    for (int u = 0; u < K / 2 - 1; u++) {
+      madc_lo_cc(Q[2 * u], a[2 * u + 1], b, Q[2 * u + 2]);
+      madc_hi_cc(Q[2 * u + 1], a[2 * u + 1], b, Q[2 * u + 3]);
+    }
+    madc_lo_cc(Q[K - 2], a[K - 1], b, t0);
+    madc_hi_cc(Q[K - 1], a[K - 1], b, t1);
+    addc(Q[K], 0, 0);
+    mad_lo_cc(P[0], a[0], b, P[0]);
+    madc_hi_cc(P[1], a[0], b, P[1]);
+#pragma unroll
+    for (int u = 1; u < K / 2; u++) {
+      madc_lo_cc(P[2 * u], a[2 * u], b, P[2 * u]);
+      madc_hi_cc(P[2 * u + 1], a[2 * u], b, P[2 * u + 1]);
+    }
+    addc(P[K], P[K], 0);
+    out = P[0];
+    uint32_t down = __shfl_down_sync(IPCLB200_FULL_MASK, P[0], 1, T);
+    return (lane_t() == T - 1) ? 0u : down;
+  }
+
+  // hi:lo = a * B (2*LH words), B = LH words at bs (shared).  The low LH words
+  // are written to los (shared, by lane 0 of the group), the high ones returned
+  // in hi (K limbs per lane).
+  __device__ __forceinline__ static void mul_plain(uint32_t (&hi)[K], const uint32_t (&a)[K],
+                                                   const uint32_t* bs, uint32_t* los) {
+    uint32_t E[K + 1], O[K + 1];
+#pragma unroll
+    for (int j = 0; j <= K; j++) {
+      E[j] = 0;
+      O[j] = 0;
+    }
+    uint32_t in_limb = 0;
+    const bool l0 = lane_t() == 0;
+#pragma unroll 1
+    for (int i = 0; i < LH; i += 4) {
+      const uint4 bv = *reinterpret_cast<const uint4*>(bs + i);
+      uint4 ov;
+      in_limb = row_plain(E, O, a, bv.x, in_limb, ov.x);
+      in_limb = row_plain(O, E, a, bv.y, in_limb, ov.y);
+      in_limb = row_plain(E, O, a, bv.z, in_limb, ov.z);
+      in_limb = row_plain(O, E, a, bv.w, in_limb, ov.w);
+      if (l0) *reinterpret_cast<uint4*>(los + i) = ov;
+    }
+    uint32_t t0, t1;
+    add_cc(t0, O[K], in_limb);
+    addc(t1, 0, 0);
+    assemble(hi, E, O, t0, t1);  // a*B < R^2: nothing above the high half
+  }
+
+  // ---- (x0, w) = sum_j (c_j, 0) * K_j : c_j = the j-th LH-word chunk at c (global),
+  //      K_j = the pair at consts + 2*j*LH (global).  With K_j = R^(j+1) in
+  //      Montgomery form this is c * R mod p^2 for the integer c = sum c_j R^j ------
+  __device__ __forceinline__ static void enter(uint32_t (&x0)[K], uint32_t (&w)[K],
+                                               const uint32_t* c, int nchunks,
+                                               const uint32_t* consts, uint32_t* sm,
+                                               const uint32_t (&n)[K], uint32_t n0inv) {
+#pragma unroll 1
+    for (int j = 0; j < nchunks; j++) {
+      uint32_t a[K], z0[K], wz[K];
+      __syncwarp();
+      M::load(a, consts + (size_t)(2 * j) * LH);
+      put(sm + kS0, a);
+      M::load(a, consts + (size_t)(2 * j + 1) * LH);
+      put(sm + kS1, a);
+      __syncwarp();
+      M::load(a, c + (size_t)j * LH);
+      mul_digit(z0, wz, a, sm, n, n0inv);
+      if (j == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          x0[k] = z0[k];
+          w[k] = wz[k];
+        }
+      } else {
+        add(x0, w, z0, wz, n);
+      }
+    }
+  }
+
   // ---- (x0, w) += (y0, wy)  (prologue only) -----------------------------------
   // Each p taken off digit 0 is one taken off w, i.e. + (p - 1).
   __device__ __forceinline__ static void add(uint32_t (&x0)[K], uint32_t (&w)[K],

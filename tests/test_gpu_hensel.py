@@ -164,3 +164,48 @@ def test_constant_schedule_mode(capi, all_keys, name, monkeypatch):
     sk.set_schedule(False)
     assert np.array_equal(sk.decrypt(ct), base)
     assert batch_from_limbs(base[:6]) == [dec_crt(p, q, c) for c in cts[:6]]
+
+
+@pytest.mark.parametrize("name", ["1024", "2048", "3072", "4096", "2048_low", "2048_high"])
+def test_hensel_encrypt_matches_oracle(capi, oracle, all_keys, name, monkeypatch):
+    """encrypt_hensel_kernel (two-digit arithmetic mod n^2 over a fixed-base table
+    of pairs) against the oracle, bit for bit: edge plaintexts 0, 1, n-1, edge
+    randoms 0, 1, 2^k, all-ones, short randoms (fewer windows), narrow plaintext
+    buffers; and the same ciphertexts from the full-width table.  2048_low has an
+    n that does not fill its words and stays on the full-width kernel."""
+    k = all_keys[name]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL = (p.bit_length() + 31) // 32 * 2
+    rb = NL * 16
+    rng = np.random.default_rng(NL + len(name))
+    count = 400
+    pts = [int.from_bytes(rng.bytes(NL * 4), "little") % n for _ in range(count)]
+    pts[:3] = [0, 1, n - 1]
+    rs = [int.from_bytes(rng.bytes(NL * 2), "little") for _ in range(count)]
+    rs[:5] = [0, 1, 1 << (rb - 1), (1 << rb) - 1, 1 << 16]
+    pt, r = batch_to_limbs(pts, NL), batch_to_limbs(rs, NL // 2)
+    nl, hsl = to_limbs(n, NL), to_limbs(k["hs"], 2 * NL)
+    monkeypatch.setenv("IPCLB200_COMB_SYNC", "1")
+    want = oracle.encrypt(nl, hsl, pt, r)
+
+    def encrypt_with(policy_mb):
+        pk = capi.PubKey(nl, hsl, rb)
+        pk.set_table_policy(max_table_mb=policy_mb, upgrade_after=0)
+        out = pk.encrypt(pt, r)
+        short = pk.encrypt(pt[:64], np.ascontiguousarray(r[:64, :2]))   # 64-bit randoms
+        narrow = pk.encrypt(np.ascontiguousarray(pt[:64, :1]), r[:64])  # 32-bit plaintexts
+        pk.close()
+        return out, short, narrow
+
+    got, short, narrow = encrypt_with(48)
+    assert np.array_equal(got, want)
+    r_short = np.zeros((64, NL // 2), dtype=np.uint32)
+    r_short[:, :2] = r[:64, :2]
+    assert np.array_equal(short, oracle.encrypt(nl, hsl, pt[:64], r_short))
+    pt_narrow = np.zeros((64, NL), dtype=np.uint32)
+    pt_narrow[:, 0] = pt[:64, 0]
+    assert np.array_equal(narrow, oracle.encrypt(nl, hsl, pt_narrow, r[:64]))
+    monkeypatch.setenv("IPCLB200_NO_HENSEL_ENCRYPT", "1")
+    got2, _, _ = encrypt_with(48)
+    assert np.array_equal(got2, want)
