@@ -393,8 +393,16 @@ struct HMont {
       put(sm + kS1, dw);
       __syncwarp();
     }
-    uint32_t z0[K];
-    const uint32_t ovA = pass_a(z0, x0, is_mul ? ys : sm + kS0, sm + kSQ, n, n0inv);
+    uint32_t ovA;
+    {
+      // digit 0 of the result waits in this lane's slice of S0 (dead after pass A:
+      // a squaring has consumed its copy of x0, a multiply reads the entry buffer)
+      // while pass B runs: 16 registers less in the hottest loop
+      uint32_t z0[K];
+      ovA = pass_a(z0, x0, is_mul ? ys : sm + kS0, sm + kSQ, n, n0inv);
+      __syncwarp();  // every lane of the group is done reading S0
+      put(sm + kS0, z0);
+    }
     if (is_mul) {
       uint32_t wz[K];
       pass_b<true>(wz, x0, w, ys + LH, ys, sm + kSQ, n, n0inv, 0u, ovA);
@@ -403,8 +411,7 @@ struct HMont {
     } else {
       pass_b<false>(w, x0, x0, sm + kS1, sm + kS1, sm + kSQ, n, n0inv, hb, ovA);
     }
-#pragma unroll
-    for (int j = 0; j < K; j++) x0[j] = z0[j];
+    M::load(x0, sm + kS0);  // this lane's own slice: no synchronisation needed
   }
 
   // ---- (x0, w) <- (a, 0) * (k0, kw), the constant pair already staged at
