@@ -195,6 +195,24 @@ inline Limbs pow2(unsigned bits) {
   return r;
 }
 // -n^{-1} mod 2^32 for odd n0 (Newton iteration on the 2-adic inverse)
+// floor(sqrt(a)) by Newton's iteration; *exact = (root^2 == a)
+inline Limbs isqrt(const Limbs& a, bool* exact) {
+  if (a.empty()) {
+    if (exact) *exact = true;
+    return a;
+  }
+  Limbs x = pow2((unsigned)((bitlen(a) + 1) / 2));  // >= sqrt(a)
+  for (;;) {
+    Limbs q;
+    divmod(a, x, &q, nullptr);
+    Limbs y = shr(add(x, q), 1);
+    if (cmp(y, x) >= 0) break;
+    x = y;
+  }
+  if (exact) *exact = cmp(mul(x, x), a) == 0;
+  return x;
+}
+
 inline uint32_t neg_inv32(uint32_t n0) {
   uint32_t x = n0;
   for (int i = 0; i < 5; i++) x *= 2u - n0 * x;

@@ -56,11 +56,15 @@ struct DevModulus {
   uint32_t* d = nullptr;  // [n | rr | r3 | one] each L words, then n0inv
   const uint32_t* d_n0inv = nullptr;
   ModConst mc{};
+  // the modulus is the square of a root that fills its LH = L/2 words (n^2 of a
+  // Paillier key): modexp_hensel_kernel applies.  d_root: root | pairs of R^2, R^3
+  int root_words = 0;
+  uint32_t* d_root = nullptr;
+  uint32_t root_n0inv = 0;
   ~DevModulus() {
-    if (d) {
-      cudaSetDevice(device);
-      cudaFree(d);
-    }
+    cudaSetDevice(device);
+    if (d) cudaFree(d);
+    if (d_root) cudaFree(d_root);
   }
 };
 
@@ -396,6 +400,32 @@ int make_modulus(Dev* dev, const Limbs& n, int L, std::shared_ptr<DevModulus>* o
   m->d_n0inv = m->d + 4 * L;
   m->mc.n0inv = h.n0inv;
   m->mc.small_mod = h.small_mod;
+  if ((L == 64 || L == 128 || L == 192 || L == 256) && hbn::bitlen(n) > 32 * (L - 1)) {
+    // a perfect square whose root fills L/2 words?  (ct * pt works mod n^2)
+    bool exact = false;
+    Limbs root = hbn::isqrt(n, &exact);
+    const int lh = L / 2;
+    if (exact && (root[0] & 1u) && hbn::bitlen(root) == 32 * lh) {
+      std::vector<uint32_t> rb(5 * (size_t)lh, 0u);
+      hbn::to_words(root, rb.data(), lh);
+      const Limbs Rh = hbn::pow2(32u * (unsigned)lh);
+      Limbs t = hbn::mod(hbn::mul(Rh, Rh), n);  // R^2
+      for (int j = 0; j < 2; j++) {
+        Limbs hi, lo;
+        hbn::divmod(t, root, &hi, &lo);
+        Limbs wneg = hbn::mod(hi, root);
+        Limbs w = hbn::is_zero(wneg) ? wneg : hbn::sub(root, wneg);
+        hbn::to_words(lo, rb.data() + (size_t)(1 + 2 * j) * lh, lh);
+        hbn::to_words(w, rb.data() + (size_t)(2 + 2 * j) * lh, lh);
+        t = hbn::mod(hbn::mul(t, Rh), n);  // R^3
+      }
+      CUDA_TRY(cudaMalloc(&m->d_root, rb.size() * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemcpy(m->d_root, rb.data(), rb.size() * sizeof(uint32_t),
+                          cudaMemcpyHostToDevice));
+      m->root_words = lh;
+      m->root_n0inv = hbn::neg_inv32(root[0]);
+    }
+  }
   std::lock_guard<std::mutex> lk(dev->mu);
   if (dev->mod_cache.size() >= 32) dev->mod_cache.erase(dev->mod_cache.begin());
   dev->mod_cache.push_back(m);
@@ -475,6 +505,55 @@ int launch_modexp(Op& op, ModexpParams p, int L) {
     default: IPCLB200_DISPATCH(L, F)
   }
 #undef F
+  g.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// modexp mod the square of dm's root in two-digit arithmetic (K1h)
+constexpr size_t kHenselModexpMin = 2048;
+bool modexp_hensel_applies(const DevModulus& dm, size_t count, int exp_bits) {
+  if (!dm.root_words || count < kHenselModexpMin || exp_bits < 1) return false;
+  const char* e = getenv("IPCLB200_NO_HENSEL_MODEXP");
+  return !(e && e[0] == '1');
+}
+
+int launch_modexp_hensel(Op& op, const DevModulus& dm, const uint32_t* d_base,
+                         const uint32_t* d_exp, size_t exp_stride, int exp_words, int exp_bits,
+                         size_t count, uint32_t* d_out) {
+  const int lh = dm.root_words;
+  ModexpHenselParams p{};
+  p.base = d_base;
+  p.exp = d_exp;
+  p.exp_stride = exp_stride;
+  p.exp_words = exp_words;
+  p.exp_bits = exp_bits;
+  p.window = pick_window(exp_bits);
+  p.blk = dm.d_root;
+  p.n0inv = dm.root_n0inv;
+  p.out = d_out;
+  p.count = count;
+#define FM(K_, T_, MINB_)                                                                \
+  {                                                                                      \
+    auto kern = modexp_hensel_kernel<K_, T_, MINB_, 8>;                                  \
+    constexpr size_t smem = hensel_smem_bytes<K_, T_>(kBlockThreads);                    \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                           \
+    int grid = 0;                                                                        \
+    TRY(grid_for(op.dev, kern, count, T_, smem, &grid));                                 \
+    const size_t groups = (size_t)grid * (kBlockThreads / T_);                           \
+    TRY(table_ws(op, groups * ((size_t)(2 * lh) << p.window), &p.table_ws,               \
+                 &p.work_counter));                                                      \
+    kern<<<grid, kBlockThreads, smem, op.s>>>(p);                                        \
+  }
+  switch (lh) {
+    case 32: FM(16, 2, 3) break;
+    case 64: FM(16, 4, 3) break;
+    case 96: FM(12, 8, 3) break;
+    case 128: FM(16, 8, 3) break;
+    default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel modexp: unsupported width");
+  }
+#undef FM
   g.launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -720,6 +799,13 @@ int modexp_shared_dev(Op& op, const uint32_t* d_base, const uint32_t* d_exp,
   std::shared_ptr<DevModulus> dm;
   TRY(make_modulus(op.dev, n, L, &dm));
   CUDA_TRY(cudaSetDevice(op.dev->id));
+  {
+    const int eb = exp_bits > 0 ? exp_bits : exp_words * 32;
+    if (!(flags & IPCLB200_SHARED_BASE) && modexp_hensel_applies(*dm, count, eb))
+      return launch_modexp_hensel(op, *dm, d_base, d_exp,
+                                  (flags & IPCLB200_SHARED_EXP) ? 0 : (size_t)exp_words,
+                                  exp_words, eb, count, d_out);
+  }
   ModexpParams p{};
   p.base = d_base;
   p.base_stride = (flags & IPCLB200_SHARED_BASE) ? 0 : L;
@@ -808,6 +894,12 @@ int modexp_host_shard(Op& op, const uint32_t* base, const uint32_t* exp, const u
   p.exp = d_exp;
   p.exp_stride = sh_exp ? 0 : exp_words;
   p.out = d_out;
+  if (sh_mod && !sh_base && mod_words == L && modexp_hensel_applies(*dm, count, exp_bits)) {
+    TRY(launch_modexp_hensel(op, *dm, d_base, d_exp, sh_exp ? 0 : (size_t)exp_words,
+                             exp_words, exp_bits, count, d_out));
+    TRY(download_padded(out, d_out, mod_words, L, count, s));
+    return 0;
+  }
   if (sched) {
     uint32_t* d_sc;
     TRY(op.words((sched->size() + 3) / 4, &d_sc));

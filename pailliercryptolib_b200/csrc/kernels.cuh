@@ -844,10 +844,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB)
       phase[b] ^= 1u;
       H::mul(x0, w, sBuf + b * kBuf, sm, n, n0inv);
     }
-    // ---- a = u0 mod n (c = 1 if n was taken off), uw mod n ---------------------
-    const uint32_t c = M::sub_n_if_ge(x0, n);
-    M::sub_n_if_ge(w, n);
-    // ---- am = a * m mod n: two half-width Montgomery products (m, then R^2) ------
+    // ---- am = a * m mod n: two half-width Montgomery products (m, then R^2).
+    // a*m only matters mod n, so the not yet reduced u0 (< R) serves as a ----------
     uint32_t t[K];
     {
       uint32_t m[K];
@@ -855,49 +853,162 @@ __global__ void __launch_bounds__(kBlockThreads, MINB)
       __syncwarp();
       H::put(sS0, m);
       __syncwarp();
-      H::pass_a(t, x0, sS0, sSQ, n, n0inv);  // a*m/R
+      H::pass_a(t, x0, sS0, sSQ, n, n0inv);  // u0*m/R
       M::load(m, p.blk + LH);
       __syncwarp();
       H::put(sS0, m);
       __syncwarp();
       uint32_t t2[K];
-      H::pass_a(t2, t, sS0, sSQ, n, n0inv);  // a*m mod n, < R
+      H::pass_a(t2, t, sS0, sSQ, n, n0inv);  // u0*m mod n, < R
 #pragma unroll
       for (int j = 0; j < K; j++) t[j] = t2[j];
     }
     M::sub_n_if_ge(t, n);
-    // ---- t = (am + c - uw) mod n --------------------------------------------------
-    {
-      uint32_t y[K];
-#pragma unroll
-      for (int j = 0; j < K; j++) y[j] = 0;
-      M::group_add(t, y, c);  // am + c <= n
-      M::sub_n_if_ge(t, n);
-#pragma unroll
-      for (int j = 0; j < K; j++) y[j] = ~w[j];
-      const uint32_t nb = M::group_add(t, y, 1u);  // t - uw; carry out <=> no borrow
-#pragma unroll
-      for (int j = 0; j < K; j++) y[j] = nb ? 0u : n[j];
-      M::group_add(t, y, 0u);  // + n after a borrow (the carry out cancels it)
-    }
-    // ---- ct = a + t*n: plain LH x LH product, low half through shared memory -------
+    // ---- ct = a + ((am + c - uw) mod n) * n ------------------------------------------
     uint32_t hi[K], lo[K];
-    __syncwarp();
-    H::put(sS0, t);
-    __syncwarp();
-    H::mul_plain(hi, n, sS0, sSQ);
-    __syncwarp();
-    M::load(lo, sSQ);  // this lane's K low limbs (shared memory, generic load)
-    {
-      const uint32_t cy = M::group_add(lo, x0, 0u);
-      uint32_t y[K];
-#pragma unroll
-      for (int j = 0; j < K; j++) y[j] = 0;
-      M::group_add(hi, y, cy);
-    }
+    H::to_canonical(lo, hi, x0, w, t, sm, n);
     if (valid) {
       M::store(p.ct + inst * (size_t)(2 * LH), lo);
       M::store(p.ct + inst * (size_t)(2 * LH) + LH, hi);
+    }
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------------
+// K1h: batched modexp mod n^2 in two-digit arithmetic, for a modulus that is
+//     the square of an n that fills its LH words (CipherText * PlainText,
+//     ipcl/ciphertext.cpp:143-162: a^b mod n^2 with per-element b).  Prologue:
+//     the 2*LH-word base -> Montgomery pair; fixed-window ladder over a table of
+//     all 2^w powers in the group's workspace slot (window entries fetched by TMA
+//     bulk copies while the squarings run); epilogue: leave Montgomery form with
+//     one product by the pair of 1, then pair -> canonical residue.
+// --------------------------------------------------------------------------
+struct ModexpHenselParams {
+  const uint32_t* base;  // count x 2*LH words (any value < R^2)
+  const uint32_t* exp;
+  size_t exp_stride;     // words, 0 = shared
+  int exp_words;
+  int exp_bits;
+  int window;
+  const uint32_t* blk;   // n | pairs of R, R^2 (Montgomery form of chunk weights 1, R)
+  uint32_t n0inv;
+  uint32_t* out;         // count x 2*LH words
+  size_t count;
+  uint32_t* table_ws;    // per group (1 << window) x 2*LH words
+  unsigned int* work_counter;
+};
+
+template <int K, int T, int MINB, int ROWS>
+__global__ void __launch_bounds__(kBlockThreads, MINB)
+    modexp_hensel_kernel(const ModexpHenselParams p) {
+  using M = Mont<K, T>;
+  using H = HMont<K, T, ROWS>;
+  constexpr int LH = K * T;
+  constexpr int GW = 32 / T;
+  extern __shared__ __align__(16) uint32_t hensel_smem[];
+  const int gib = threadIdx.x / T;
+  uint32_t* sm = hensel_smem + (size_t)gib * H::kStride;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hensel_smem +
+                                              (size_t)(blockDim.x / T) * H::kStride) +
+                  (threadIdx.x >> 5);
+  const bool warp_leader = (threadIdx.x & 31) == 0;
+  const bool group_leader = M::lane_t() == 0;
+  if (warp_leader) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase = 0;
+  const size_t gid = (size_t)blockIdx.x * (blockDim.x / T) + gib;
+  const int w = p.window;
+  uint32_t* tab = p.table_ws + gid * ((size_t)(2 * LH) << w);
+  constexpr uint32_t kEntryBytes = 2 * LH * sizeof(uint32_t);
+  const unsigned int nchunks = (unsigned int)((p.count + GW - 1) / GW);
+  uint32_t n[K];
+  M::load(n, p.blk);
+  const uint32_t n0inv = p.n0inv;
+  int nwin = (p.exp_bits + w - 1) / w;
+  if (nwin < 1) nwin = 1;
+  for (;;) {
+    const unsigned int wk = claim_chunk(p.work_counter);
+    if (wk >= nchunks) break;
+    const size_t inst = (size_t)wk * GW + (threadIdx.x & 31) / T;
+    const bool valid = inst < p.count;
+    const size_t ii = valid ? inst : p.count - 1;
+    const uint32_t* e = p.exp + ii * p.exp_stride;
+    uint32_t x0[K], xw[K];
+    H::enter(x0, xw, p.base + ii * (size_t)(2 * LH), 2, p.blk + LH, sm, n, n0inv);
+    // ---- table: x^0 = 1 as the pair (R - n, n - 1), x^1, x^i = x^(i-1) * x ---------
+    {
+      uint32_t o0[K], o1[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        o0[j] = ~n[j];
+        o1[j] = n[j];
+      }
+      if (M::lane_t() == 0) {
+        o0[0] += 1u;
+        o1[0] -= 1u;
+      }
+      M::store(tab, o0);
+      M::store(tab + LH, o1);
+      M::store(tab + 2 * LH, x0);
+      M::store(tab + 3 * LH, xw);
+      __syncwarp();
+      H::put(sm + H::kT0, x0);
+      H::put(sm + H::kT0 + LH, xw);
+      __syncwarp();
+#pragma unroll 1
+      for (int i = 2; i < (1 << w); i++) {
+        H::step(x0, xw, true, sm + H::kT0, sm, n, n0inv);
+        M::store(tab + (size_t)i * 2 * LH, x0);
+        M::store(tab + (size_t)i * 2 * LH + LH, xw);
+      }
+    }
+    // ---- ladder -------------------------------------------------------------------
+    {
+      const uint32_t first = exp_window(e, p.exp_words, nwin - 1, w);
+      M::load(x0, tab + (size_t)first * 2 * LH);
+      M::load(xw, tab + (size_t)first * 2 * LH + LH);
+    }
+#pragma unroll 1
+    for (int k = nwin - 2; k >= 0; k--) {
+      __syncwarp();
+      fence_async_proxy();
+      if (warp_leader) mbar_expect_tx(bar, GW * kEntryBytes);
+      __syncwarp();
+      if (group_leader)
+        bulk_g2s(sm + H::kT0, tab + (size_t)exp_window(e, p.exp_words, k, w) * 2 * LH,
+                 kEntryBytes, bar);
+#pragma unroll 1
+      for (int sq = 0; sq <= w; sq++) {
+        const bool is_mul = sq == w;
+        if (is_mul) {
+          mbar_wait(bar, phase);
+          phase ^= 1u;
+        }
+        H::step(x0, xw, is_mul, sm + H::kT0, sm, n, n0inv);
+      }
+    }
+    // ---- leave Montgomery form: times the raw pair (1, 0), then canonical -------------
+    {
+      uint32_t one[K], zero[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        one[j] = 0;
+        zero[j] = 0;
+      }
+      if (M::lane_t() == 0) one[0] = 1;
+      __syncwarp();
+      H::put(sm + H::kT0, one);
+      H::put(sm + H::kT0 + LH, zero);
+      __syncwarp();
+      H::step(x0, xw, true, sm + H::kT0, sm, n, n0inv);
+      uint32_t lo[K], hi[K];
+      H::to_canonical(lo, hi, x0, xw, zero, sm, n);
+      if (valid) {
+        M::store(p.out + inst * (size_t)(2 * LH), lo);
+        M::store(p.out + inst * (size_t)(2 * LH) + LH, hi);
+      }
     }
     __syncwarp();
   }

@@ -514,6 +514,42 @@ struct HMont {
     }
   }
 
+  // ---- plain pair -> canonical residue: for u = u0 - uw*n (mod n^2) and an
+  //      extra digit-1 term `am` (< n, canonical): with a = u0 mod n (u0 = a + c*n)
+  //          u + am*n = a + ((am + c - uw) mod n) * n        (mod n^2)
+  //      lo | hi = the 2*LH-word result.  S0 and SQ of the group area are scratch.
+  __device__ __forceinline__ static void to_canonical(uint32_t (&lo)[K], uint32_t (&hi)[K],
+                                                      uint32_t (&u0)[K], uint32_t (&uw)[K],
+                                                      uint32_t (&am)[K], uint32_t* sm,
+                                                      const uint32_t (&n)[K]) {
+    const uint32_t c = M::sub_n_if_ge(u0, n);
+    M::sub_n_if_ge(uw, n);
+    {
+      uint32_t y[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = 0;
+      M::group_add(am, y, c);  // am + c <= n
+      M::sub_n_if_ge(am, n);
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = ~uw[j];
+      const uint32_t nb = M::group_add(am, y, 1u);  // - uw; carry out <=> no borrow
+#pragma unroll
+      for (int j = 0; j < K; j++) y[j] = nb ? 0u : n[j];
+      M::group_add(am, y, 0u);  // + n after a borrow (the carry out cancels it)
+    }
+    __syncwarp();
+    put(sm + kS0, am);
+    __syncwarp();
+    mul_plain(hi, n, sm + kS0, sm + kSQ);
+    __syncwarp();
+    M::load(lo, sm + kSQ);  // this lane's K low limbs
+    const uint32_t cy = M::group_add(lo, u0, 0u);
+    uint32_t y[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) y[j] = 0;
+    M::group_add(hi, y, cy);
+  }
+
   // ---- (x0, w) += (y0, wy)  (prologue only) -----------------------------------
   // Each p taken off digit 0 is one taken off w, i.e. + (p - 1).
   __device__ __forceinline__ static void add(uint32_t (&x0)[K], uint32_t (&w)[K],

@@ -209,3 +209,47 @@ def test_hensel_encrypt_matches_oracle(capi, oracle, all_keys, name, monkeypatch
     monkeypatch.setenv("IPCLB200_NO_HENSEL_ENCRYPT", "1")
     got2, _, _ = encrypt_with(48)
     assert np.array_equal(got2, want)
+
+
+@pytest.mark.parametrize("name", ["1024", "2048", "3072", "4096"])
+def test_hensel_modexp_square_modulus_vs_oracle(capi, oracle, all_keys, name, monkeypatch):
+    """modexp_hensel_kernel: a batch of a^b mod n^2 (CipherText * PlainText) when the
+    modulus is the square of an n that fills its words.  Per-element exponents of
+    1 ... 70 bits and of full width, a shared exponent, bases 0, 1, n^2-1 and
+    unreduced ones up to 2^(32L)-1; against the oracle and against the full-width
+    kernel (IPCLB200_NO_HENSEL_MODEXP=1)."""
+    k = all_keys[name]
+    n = k["p"] * k["q"]
+    nsq = n * n
+    L = (nsq.bit_length() + 31) // 32
+    rng = np.random.default_rng(L)
+    count = 2100
+    top = 1 << (32 * L)
+    bases = [int.from_bytes(rng.bytes(4 * L), "little") % nsq for _ in range(count)]
+    bases[:6] = [0, 1, nsq - 1, n, top - 1, nsq + 12345]
+    base = batch_to_limbs(bases, L)
+    mod = to_limbs(nsq, L)
+    # small exponents, every bit length from 1 to 70
+    exps = [(int.from_bytes(rng.bytes(9), "little") >> (72 - 1 - i % 70)) | 1 for i in range(count)]
+    exps[:3] = [0, 1, 2]
+    e_small = batch_to_limbs(exps, 3)
+    monkeypatch.delenv("IPCLB200_NO_HENSEL_MODEXP", raising=False)
+    got = capi.modexp(base, e_small, mod, capi.SHARED_MOD)
+    want = oracle.modexp(base, e_small, mod[None, :], shared_mod=True)
+    assert np.array_equal(got, want)
+    assert batch_from_limbs(got[:8]) == [pow(b, e, nsq) for b, e in zip(bases[:8], exps[:8])]
+    # shared exponent
+    e_sh = to_limbs(0xC0FFEE1234567, 2)
+    got_sh = capi.modexp(base, e_sh, mod, capi.SHARED_MOD | capi.SHARED_EXP)
+    assert batch_from_limbs(got_sh[:40]) == [pow(b, 0xC0FFEE1234567, nsq) for b in bases[:40]]
+    monkeypatch.setenv("IPCLB200_NO_HENSEL_MODEXP", "1")
+    assert np.array_equal(capi.modexp(base, e_small, mod, capi.SHARED_MOD), want)
+    assert np.array_equal(capi.modexp(base, e_sh, mod, capi.SHARED_MOD | capi.SHARED_EXP), got_sh)
+    monkeypatch.delenv("IPCLB200_NO_HENSEL_MODEXP")
+    # full-width exponents (the benchmark shape of ct*pt), a sample against pow()
+    e_full = random_limbs(rng, count, L // 2)
+    got_full = capi.modexp(base, e_full, mod, capi.SHARED_MOD)
+    ef = batch_from_limbs(e_full[:10])
+    assert batch_from_limbs(got_full[:10]) == [pow(b, e, nsq) for b, e in zip(bases[:10], ef)]
+    monkeypatch.setenv("IPCLB200_NO_HENSEL_MODEXP", "1")
+    assert np.array_equal(capi.modexp(base, e_full, mod, capi.SHARED_MOD), got_full)
