@@ -154,6 +154,27 @@ int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt,
                          size_t count, int make_secure, uint32_t* d_ct,
                          void* stream);
 
+/* ---- DJN randoms drawn on the device ------------------------------------------
+ * The reference draws r = getRandomBN(randbits) per element on the host
+ * (ipcl/pub_key.cpp:59-61 -> ipcl/utils/common.cpp:42-101: RDSEED / RDRAND /
+ * ippsPRNGen).  Here the host supplies one fresh 256-bit key per call (OS
+ * entropy, the ipcl:: layer) and the r of the whole batch are ChaCha20
+ * keystream generated in HBM: the block function of RFC 8439 section 2.3 (20
+ * rounds) under key[8] / nonce[3] (little-endian words); element e takes the
+ * blocks with counters e*bpe .. e*bpe+bpe-1, bpe = ceil(words/16), truncated
+ * to `bits` bits (higher words zero).  No r crosses PCIe.
+ *   random_dev    : d_out = count x words on the current device; first_element
+ *                   is the global index of element 0 (a shard of a batch)
+ *   batch_random  : every shard of a batch (element indices are global)
+ *   encrypt_drbg  : ipclb200_encrypt for a DJN key with r drawn this way
+ *                   (randbits of the key), host plaintexts in, ciphertexts out */
+int ipclb200_random_dev(uint32_t* d_out, size_t count, int words, int bits,
+                        const uint32_t* key, const uint32_t* nonce,
+                        uint64_t first_element, void* stream);
+int ipclb200_encrypt_drbg(const ipclb200_pubkey* pk, const uint32_t* pt,
+                          int pt_words, size_t count, const uint32_t* key,
+                          const uint32_t* nonce, uint32_t* ct);
+
 /* ---- Paillier private key: decrypt ------------------------------------------
  * Derives p^2, q^2, p^-1 mod q, hp, hq (and lambda, x for the non-CRT path)
  * exactly as the PrivateKey constructor does, ipcl/pri_key.cpp:13-37,159-167.
@@ -246,6 +267,8 @@ int ipclb200_batch_sync(const ipclb200_batch* b);
  * work enqueued on the shard; a caller that enqueues kernels of its own there
  * calls batch_touch afterwards so that later library calls wait for them */
 int ipclb200_batch_touch(const ipclb200_batch* b, int shard, void* stream);
+int ipclb200_batch_random(ipclb200_batch* out, int bits, const uint32_t* key,
+                          const uint32_t* nonce);
 int ipclb200_batch_scatter(ipclb200_batch* b, const uint32_t* d_src);
 int ipclb200_batch_gather(const ipclb200_batch* b, uint32_t* d_dst);
 int ipclb200_encrypt_batch(const ipclb200_pubkey* pk, const ipclb200_batch* pt,

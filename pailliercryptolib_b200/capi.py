@@ -44,6 +44,7 @@ EXPORTS = [
     "ipclb200_encrypt_batch", "ipclb200_decrypt_batch", "ipclb200_modmul_batch",
     "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
     "ipclb200_batch_touch", "ipclb200_privkey_set_schedule",
+    "ipclb200_random_dev", "ipclb200_batch_random", "ipclb200_encrypt_drbg",
 ]
 
 
@@ -184,6 +185,19 @@ class PubKey:
                                       int(make_secure), _p(ct)))
         return ct
 
+    def encrypt_drbg(self, pt, key, nonce, out=None):
+        """DJN encrypt with the r of the batch drawn on the device: ChaCha20
+        keystream under key (8 words) / nonce (3 words)"""
+        pt = np.atleast_2d(_c(pt))
+        key, nonce = _c(key), _c(nonce)
+        assert key.shape == (8,) and nonce.shape == (3,)
+        ct = out if out is not None else np.zeros(
+            (pt.shape[0], 2 * self.n_words), dtype=np.uint32)
+        _check(lib().ipclb200_encrypt_drbg(self._h, _p(pt), pt.shape[1],
+                                           ctypes.c_size_t(pt.shape[0]), _p(key),
+                                           _p(nonce), _p(ct)))
+        return ct
+
     def set_table_policy(self, max_table_mb=-1, upgrade_after=-1):
         _check(lib().ipclb200_pubkey_set_table_policy(
             self._h, ctypes.c_long(max_table_mb), ctypes.c_long(upgrade_after)))
@@ -275,6 +289,14 @@ def modexp_dev(d_base, d_exp, mod, exp_words, exp_bits, count, d_out, stream,
                                      _vp(stream)))
 
 
+def random_dev(d_out, count, words, bits, key, nonce, first_element, stream):
+    key, nonce = _c(key), _c(nonce)
+    assert key.shape == (8,) and nonce.shape == (3,)
+    _check(lib().ipclb200_random_dev(_vp(d_out), ctypes.c_size_t(count), int(words),
+                                     int(bits), _p(key), _p(nonce),
+                                     ctypes.c_uint64(first_element), _vp(stream)))
+
+
 def modmul_dev(d_a, d_b, mod, count, d_out, stream, flags=0):
     mod = _c(mod)
     _check(lib().ipclb200_modmul_dev(_vp(d_a), _vp(d_b), _p(mod), mod.shape[-1],
@@ -312,6 +334,12 @@ class Batch:
 
     def sync(self):
         _check(lib().ipclb200_batch_sync(self._h))
+
+    def random(self, bits, key, nonce):
+        """fill with ChaCha20 keystream truncated to `bits` bits per element"""
+        key, nonce = _c(key), _c(nonce)
+        assert key.shape == (8,) and nonce.shape == (3,)
+        _check(lib().ipclb200_batch_random(self._h, int(bits), _p(key), _p(nonce)))
 
     def scatter_from(self, d_src):
         _check(lib().ipclb200_batch_scatter(self._h, _vp(d_src)))

@@ -1356,6 +1356,8 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
     case 32:
       if (spread >= 2) FH(4, 8, 3, 8)
       else if (spread == 1) FH(8, 4, 3, 8)
+      else if (spread == -1 && rows == 4) FH(32, 1, 2, 4)
+      else if (spread == -1) FH(32, 1, 2, 8)
       else if (rows == 4) FH(16, 2, 3, 4)
       else if (rows == 16) FH(16, 2, 3, 16)
       else FH(16, 2, 3, 8)
@@ -1637,6 +1639,38 @@ int modmul_on(Op& op, const uint32_t* d_a, const uint32_t* d_b, const Limbs& n, 
   p.out = d_out;
   p.count = count;
   return launch_modmul(op, p, L);
+}
+
+
+// r of a batch as ChaCha20 keystream (chacha20_fill_kernel, kernels.cuh K6)
+int random_fill(Op& op, uint32_t* d_out, size_t count, int words, int bits, const uint32_t* key,
+                const uint32_t* nonce, uint64_t first) {
+  if (count == 0) return 0;
+  ChachaParams p{};
+  for (int i = 0; i < 8; i++) p.key[i] = key[i];
+  for (int i = 0; i < 3; i++) p.nonce[i] = nonce[i];
+  p.out = d_out;
+  p.count = count;
+  p.first = first;
+  p.words = words;
+  p.bits = bits;
+  p.bpe = (words + 15) / 16;
+  if ((first + count) * (uint64_t)p.bpe > 0xffffffffull)
+    return fail(IPCLB200_ERR_BAD_ARG, "random: block counter exceeds 32 bits");
+  CUDA_TRY(cudaSetDevice(op.dev->id));
+  const size_t blocks = count * (size_t)p.bpe;
+  chacha20_fill_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, op.s>>>(p);
+  g.launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int check_random_args(const char* who, int words, int bits, const uint32_t* key,
+                      const uint32_t* nonce) {
+  if (!key || !nonce) return fail(IPCLB200_ERR_BAD_ARG, std::string(who) + ": null key or nonce");
+  if (words <= 0 || words > 2 * IPCLB200_MAX_MOD_WORDS || bits <= 0 || bits > 32 * words)
+    return fail(IPCLB200_ERR_BAD_ARG, std::string(who) + ": words/bits out of range");
+  return 0;
 }
 
 }  // namespace
@@ -1992,6 +2026,73 @@ int ipclb200_encrypt_dev(const ipclb200_pubkey* pk, const uint32_t* d_pt, int pt
   TRY(op.open_on(dev, (cudaStream_t)stream));
   return encrypt_dev_impl(op, pk, d_pt, pt_words, d_r, r_words, r_words * 32, count,
                           make_secure, d_ct);
+}
+
+// ---- DJN randoms drawn on the device ----------------------------------------
+int ipclb200_random_dev(uint32_t* d_out, size_t count, int words, int bits,
+                        const uint32_t* key, const uint32_t* nonce, uint64_t first_element,
+                        void* stream) {
+  if (!d_out) return fail(IPCLB200_ERR_BAD_ARG, "random_dev: null pointer");
+  TRY(check_random_args("random_dev", words, bits, key, nonce));
+  if (count == 0) return 0;
+  Dev* dev = nullptr;
+  TRY(dev_of_pointer(d_out, &dev));
+  Op op;
+  TRY(op.open_on(dev, (cudaStream_t)stream));
+  return random_fill(op, d_out, count, words, bits, key, nonce, first_element);
+}
+
+int ipclb200_batch_random(ipclb200_batch* out, int bits, const uint32_t* key,
+                          const uint32_t* nonce) {
+  if (!out) return fail(IPCLB200_ERR_BAD_ARG, "batch_random: null pointer");
+  TRY(check_random_args("batch_random", out->words, bits, key, nonce));
+  DeviceGuard guard;
+  for (size_t i = 0; i < out->shards.size(); i++) {
+    const Shard& sh = out->shards[i];
+    if (sh.count == 0) continue;
+    Op op;
+    cudaStream_t bs = nullptr;
+    TRY(batch_stream({out}, i, sh.dev, &bs));
+    TRY(op.open_on(sh.dev, bs));
+    TRY(random_fill(op, out->d[i], sh.count, out->words, bits, key, nonce, sh.begin));
+    TRY(batch_touch({out}, i, bs));
+  }
+  return 0;
+}
+
+int ipclb200_encrypt_drbg(const ipclb200_pubkey* pk, const uint32_t* pt, int pt_words,
+                          size_t count, const uint32_t* key, const uint32_t* nonce,
+                          uint32_t* ct) {
+  if (!pk || !pt || !ct) return fail(IPCLB200_ERR_BAD_ARG, "encrypt_drbg: null pointer");
+  if (!pk->djn || pk->rand_bits <= 0)
+    return fail(IPCLB200_ERR_UNSUPPORTED, "encrypt_drbg: needs a DJN key");
+  if (pt_words <= 0 || pt_words > pk->nl)
+    return fail(IPCLB200_ERR_BAD_ARG, "encrypt_drbg: pt_words out of range");
+  const int r_words = (pk->rand_bits + 31) / 32;
+  TRY(check_random_args("encrypt_drbg", r_words, pk->rand_bits, key, nonce));
+  if (count == 0) return 0;
+  DeviceGuard guard;
+  const int L = pk->L, CW = 2 * pk->nl;
+  std::vector<Shard> shards;
+  TRY(plan_shards(count, &shards));
+  std::vector<Op> ops(shards.size());
+  for (size_t i = 0; i < shards.size(); i++) {
+    const Shard& sh = shards[i];
+    Op& op = ops[i];
+    TRY(op.open(sh.dev));
+    uint32_t *d_pt, *d_r, *d_ct;
+    TRY(op.words(sh.count * (size_t)pt_words, &d_pt));
+    TRY(op.words(sh.count * (size_t)r_words, &d_r));
+    TRY(op.words(sh.count * (size_t)L, &d_ct));
+    CUDA_TRY(cudaMemcpyAsync(d_pt, pt + sh.begin * (size_t)pt_words,
+                             sh.count * (size_t)pt_words * 4, cudaMemcpyHostToDevice, op.s));
+    TRY(random_fill(op, d_r, sh.count, r_words, pk->rand_bits, key, nonce, sh.begin));
+    TRY(encrypt_dev_impl(op, pk, d_pt, pt_words, d_r, r_words, pk->rand_bits, sh.count, 1,
+                         d_ct));
+    TRY(download_padded(ct + sh.begin * (size_t)CW, d_ct, CW, L, sh.count, op.s));
+  }
+  for (auto& op : ops) TRY(op.sync());
+  return 0;
 }
 
 // ---- private key ------------------------------------------------------------

@@ -1364,4 +1364,79 @@ __global__ void int_peak_row_kernel(uint32_t* out, uint32_t a0, uint32_t b0) {
 }
 
 
+// --------------------------------------------------------------------------
+// K6: the DJN randoms of a batch drawn on the device.  The reference draws
+//     r = getRandomBN(randbits) per element on the host (ipcl/pub_key.cpp:59-61,
+//     ipcl/utils/common.cpp:42-101: RDSEED/RDRAND/IPP PRNG); here the host
+//     supplies only a fresh 256-bit key from the OS entropy pool and the r of
+//     the whole batch are the ChaCha20 keystream under it (the block function
+//     of RFC 8439 section 2.3, 20 rounds): element e takes the blocks with
+//     counters e*bpe .. e*bpe + bpe-1, bpe = ceil(words/16), truncated to
+//     `bits` bits.  One thread per 64-byte block, 128-bit stores.
+// --------------------------------------------------------------------------
+struct ChachaParams {
+  uint32_t key[8];
+  uint32_t nonce[3];
+  uint32_t* out;         // count x words
+  size_t count;          // elements of this launch
+  uint64_t first;        // global index of element 0 (shards of one batch)
+  int words, bits, bpe;  // bpe = blocks per element
+};
+
+__device__ __forceinline__ void chacha_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  a += b; d ^= a; d = __funnelshift_l(d, d, 16);
+  c += d; b ^= c; b = __funnelshift_l(b, b, 12);
+  a += b; d ^= a; d = __funnelshift_l(d, d, 8);
+  c += d; b ^= c; b = __funnelshift_l(b, b, 7);
+}
+
+__global__ void __launch_bounds__(256) chacha20_fill_kernel(const ChachaParams p) {
+  const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t e = blk / (size_t)p.bpe;
+  const int j = (int)(blk % (size_t)p.bpe);
+  if (e >= p.count) return;
+  uint32_t in[16], x[16];
+  in[0] = 0x61707865u; in[1] = 0x3320646eu; in[2] = 0x79622d32u; in[3] = 0x6b206574u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) in[4 + i] = p.key[i];
+  in[12] = (uint32_t)((p.first + e) * (uint64_t)p.bpe + (uint64_t)j);
+  in[13] = p.nonce[0]; in[14] = p.nonce[1]; in[15] = p.nonce[2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = in[i];
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    chacha_qr(x[0], x[4], x[8], x[12]);
+    chacha_qr(x[1], x[5], x[9], x[13]);
+    chacha_qr(x[2], x[6], x[10], x[14]);
+    chacha_qr(x[3], x[7], x[11], x[15]);
+    chacha_qr(x[0], x[5], x[10], x[15]);
+    chacha_qr(x[1], x[6], x[11], x[12]);
+    chacha_qr(x[2], x[7], x[8], x[13]);
+    chacha_qr(x[3], x[4], x[9], x[14]);
+  }
+  // word w of the element is word w - 16*j of this block; bits above `bits` are zero
+  uint32_t* dst = p.out + e * (size_t)p.words + (size_t)16 * j;
+  const int w0 = 16 * j;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int w = w0 + i;
+    uint32_t v = x[i] + in[i];
+    const int left = p.bits - 32 * w;  // bits of this word that are kept
+    if (left <= 0) v = 0;
+    else if (left < 32) v &= (1u << left) - 1u;
+    x[i] = v;
+  }
+  if ((p.words & 3) == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      if (w0 + i < p.words)
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      if (w0 + i < p.words) dst[i] = x[i];
+  }
+}
+
+
 }  // namespace ipclb200

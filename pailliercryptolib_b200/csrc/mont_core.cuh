@@ -160,12 +160,12 @@ struct Mont {
   // ballot look-ahead and returns the carry out of the top lane.
   __device__ __forceinline__ static uint32_t resolve(uint32_t (&r)[K],
                                                      uint32_t g) {
+    if (T == 1) return g;
     uint32_t all = r[0];
 #pragma unroll
     for (int j = 1; j < K; j++) all &= r[j];
     uint32_t bg = __ballot_sync(IPCLB200_FULL_MASK, g != 0);
     uint32_t bp = __ballot_sync(IPCLB200_FULL_MASK, all == 0xffffffffu);
-    if (T == 1) return g;
     const int sh = group_shift();
     const uint32_t gm = (T == 32) ? 0xffffffffu : ((1u << T) - 1u);
     uint64_t gg = (bg >> sh) & gm;

@@ -143,7 +143,7 @@ struct HMont {
       addc(Q[K], Q[K], 0);
     }
     uint32_t q = (MODE == 0 ? P[0] : P[0] + mi) * n0inv;
-    q = __shfl_sync(IPCLB200_FULL_MASK, q, 0, T);
+    if (T > 1) q = __shfl_sync(IPCLB200_FULL_MASK, q, 0, T);
     qout = q;
     mad_lo_cc(P[0], n[0], q, P[0]);
     madc_hi_cc(P[1], n[0], q, P[1]);
@@ -167,6 +167,7 @@ struct HMont {
       madc_hi_cc(Q[2 * u + 1], n[2 * u + 1], q, Q[2 * u + 1]);
     }
     addc(Q[K], Q[K], 0);
+    if (T == 1) return 0u;  // one lane holds the whole digit: nothing crosses
     uint32_t down = __shfl_down_sync(IPCLB200_FULL_MASK, P[0], 1, T);
     return (lane_t() == T - 1) ? 0u : down;
   }
@@ -184,6 +185,7 @@ struct HMont {
     for (int j = 1; j < K - 1; j++) addc_cc(r[j], E[j], O[j + 1]);
     addc_cc(r[K - 1], E[K - 1], t0);
     addc(ov, E[K], t1);
+    if (T == 1) return ov;  // the lane's own overflow limb is the multiple of R
     uint32_t ov_in = __shfl_up_sync(IPCLB200_FULL_MASK, ov, 1, T);
     if (lane_t() == 0) ov_in = 0;
     add_cc(r[0], r[0], ov_in);
@@ -341,12 +343,16 @@ struct HMont {
     uint32_t hb;
     {
       uint32_t dw[K];
-      uint32_t below = __shfl_up_sync(IPCLB200_FULL_MASK, w[K - 1], 1, T);
-      if (lane_t() == 0) below = 0;
+      uint32_t below = 0;
+      if (T > 1) {
+        below = __shfl_up_sync(IPCLB200_FULL_MASK, w[K - 1], 1, T);
+        if (lane_t() == 0) below = 0;
+      }
       dw[0] = __funnelshift_l(below, w[0], 1);
 #pragma unroll
       for (int j = 1; j < K; j++) dw[j] = __funnelshift_l(w[j - 1], w[j], 1);
-      hb = __shfl_sync(IPCLB200_FULL_MASK, w[K - 1] >> 31, T - 1, T);
+      hb = w[K - 1] >> 31;
+      if (T > 1) hb = __shfl_sync(IPCLB200_FULL_MASK, hb, T - 1, T);
       __syncwarp();
       put(sm + kS0, x0);
       put(sm + kS1, dw);
@@ -382,12 +388,16 @@ struct HMont {
     uint32_t hb = 0;
     if (!is_mul) {
       uint32_t dw[K];
-      uint32_t below = __shfl_up_sync(IPCLB200_FULL_MASK, w[K - 1], 1, T);
-      if (lane_t() == 0) below = 0;
+      uint32_t below = 0;
+      if (T > 1) {
+        below = __shfl_up_sync(IPCLB200_FULL_MASK, w[K - 1], 1, T);
+        if (lane_t() == 0) below = 0;
+      }
       dw[0] = __funnelshift_l(below, w[0], 1);
 #pragma unroll
       for (int j = 1; j < K; j++) dw[j] = __funnelshift_l(w[j - 1], w[j], 1);
-      hb = __shfl_sync(IPCLB200_FULL_MASK, w[K - 1] >> 31, T - 1, T);
+      hb = w[K - 1] >> 31;
+      if (T > 1) hb = __shfl_sync(IPCLB200_FULL_MASK, hb, T - 1, T);
       __syncwarp();
       put(sm + kS0, x0);
       put(sm + kS1, dw);
@@ -451,6 +461,7 @@ struct HMont {
     }
     addc(P[K], P[K], 0);
     out = P[0];
+    if (T == 1) return 0u;
     uint32_t down = __shfl_down_sync(IPCLB200_FULL_MASK, P[0], 1, T);
     return (lane_t() == T - 1) ? 0u : down;
   }

@@ -77,7 +77,8 @@ class PublicKey {
   mutable std::shared_ptr<DeviceKey> m_dev;
   ipclb200_pubkey* deviceKey() const;
   void flatRandoms(std::size_t sz, std::vector<uint32_t>& f_r, int& r_words) const;
-  void resetDeviceKey() { m_dev.reset(); }
+  void resetDeviceKey();
+  bool deviceRandoms() const;
 
   std::vector<BigNumber> raw_encrypt(const std::vector<BigNumber>& pt,
                                      bool make_secure = true) const;

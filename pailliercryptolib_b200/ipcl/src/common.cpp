@@ -5,16 +5,25 @@
 
 #include <sys/random.h>
 
+#include <cerrno>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+
+#include "drbg.hpp"
 
 namespace ipcl {
 
 static void fill_random(void* p, std::size_t n) {
   unsigned char* b = static_cast<unsigned char*>(p);
   while (n) {
-    ssize_t got = getrandom(b, n, 0);
-    if (got < 0) throw std::runtime_error("getrandom failed");
+    // the kernel hands out at most 32 MB - 1 per call and may be interrupted by a
+    // signal on requests over 256 bytes
+    ssize_t got = getrandom(b, n < (1u << 24) ? n : (1u << 24), 0);
+    if (got < 0) {
+      if (errno == EINTR) continue;
+      throw std::runtime_error("getrandom failed");
+    }
     b += got;
     n -= static_cast<std::size_t>(got);
   }
@@ -31,5 +40,24 @@ BigNumber getRandomBN(int bits) {
   if (bits % 32) w.back() &= (1u << (bits % 32)) - 1u;
   return BigNumber(w.data(), static_cast<int>(w.size()));
 }
+
+namespace detail {
+
+void freshDrbgSeed(uint32_t (&key)[8], uint32_t (&nonce)[3]) {
+  uint32_t buf[11];
+  fill_random(buf, sizeof(buf));
+  std::memcpy(key, buf, sizeof(key));
+  std::memcpy(nonce, buf + 8, sizeof(nonce));
+}
+
+bool deviceRandomEnabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("IPCL_B200_DEVICE_RANDOM");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+}  // namespace detail
 
 }  // namespace ipcl

@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "device_batch.hpp"
+#include "drbg.hpp"
 #include "ipcl/ciphertext.hpp"
 #include "ipcl/mod_exp.hpp"
 #include "ipcl/utils/util.hpp"
@@ -18,16 +19,21 @@
 
 namespace ipcl {
 
+// The device-side key is built lazily, on the first encrypt.  The holder is
+// allocated when the key VALUE is set (constructor, create, setHS ...), so every
+// copy of a PublicKey taken afterwards -- each CipherText stores one
+// (ipcl/ciphertext.cpp:14) -- shares the one device key and its fixed-base table
+// instead of building its own.
 struct PublicKey::DeviceKey {
+  std::mutex mu;  // guards lazy creation; encrypt() is const and is called
+                  // concurrently on one key (test/test_cryptography.cpp:45-57)
   ipclb200_pubkey* h = nullptr;
   ~DeviceKey() {
     if (h) ipclb200_pubkey_destroy(h);
   }
 };
 
-static std::mutex g_pk_mutex;  // guards lazy creation; encrypt() is const and
-                               // is called concurrently on one key
-                               // (test/test_cryptography.cpp:45-57)
+void PublicKey::resetDeviceKey() { m_dev = std::make_shared<DeviceKey>(); }
 
 PublicKey::PublicKey(const BigNumber& n, int bits, bool enableDJN_)
     : m_n(std::make_shared<BigNumber>(n)),
@@ -39,6 +45,7 @@ PublicKey::PublicKey(const BigNumber& n, int bits, bool enableDJN_)
       m_randbits(0),
       m_enable_DJN(false),
       m_testv(false) {
+  resetDeviceKey();
   if (enableDJN_) this->enableDJN();
   m_isInitialized = true;
 }
@@ -102,9 +109,10 @@ void PublicKey::create(const BigNumber& n, int bits, const BigNumber& hs,
 }
 
 ipclb200_pubkey* PublicKey::deviceKey() const {
-  std::lock_guard<std::mutex> lk(g_pk_mutex);
-  if (!m_dev) {
-    auto dk = std::make_shared<DeviceKey>();
+  ERROR_CHECK(m_dev != nullptr, "encrypt: Public key is NOT initialized.");
+  std::lock_guard<std::mutex> lk(m_dev->mu);
+  if (!m_dev->h) {
+    DeviceKey* dk = m_dev.get();
     const int nl = static_cast<int>(m_n->words().size());
     std::vector<uint32_t> n_w(static_cast<std::size_t>(nl));
     m_n->toWords(n_w.data(), n_w.size());
@@ -117,7 +125,6 @@ ipclb200_pubkey* PublicKey::deviceKey() const {
     DEVICE_CHECK(ipclb200_pubkey_create(n_w.data(), nl,
                                         m_enable_DJN ? hs_w.data() : nullptr,
                                         m_randbits, &dk->h));
-    m_dev = dk;
   }
   return m_dev->h;
 }
@@ -182,10 +189,22 @@ void PublicKey::flatRandoms(std::size_t sz, std::vector<uint32_t>& f_r,
   std::vector<BigNumber> r = drawRandoms(sz);
   for (auto& x : r) {
     ERROR_CHECK(!x.isNegative(), "encrypt: negative random");
-    if (static_cast<int>(x.words().size()) > 2 * nl) x = x % (*m_nsquare);
+    if (static_cast<int>(x.words().size()) > 2 * nl) {
+      // r is the BASE of r^n for a non-DJN key: r mod n^2 gives the same
+      // obfuscator.  For a DJN key it is the EXPONENT of hs^r and must not be
+      // reduced (hs^(r mod n^2) != hs^r)
+      ERROR_CHECK(!m_enable_DJN,
+                  "encrypt: injected DJN random is wider than n^2");
+      x = x % (*m_nsquare);
+    }
   }
   r_words = detail::maxWords(r);
   detail::pack(r, r_words, f_r);
+}
+
+// fresh DJN randoms (not injected by setRandom) are drawn on the device
+bool PublicKey::deviceRandoms() const {
+  return m_enable_DJN && !m_testv && m_randbits > 0 && detail::deviceRandomEnabled();
 }
 
 // (n*pt + 1) mod n^2 only depends on pt mod n: negative or oversize plaintexts
@@ -216,6 +235,12 @@ std::vector<BigNumber> PublicKey::raw_encrypt(const std::vector<BigNumber>& pt,
       f_ct(sz * 2 * static_cast<std::size_t>(nl));
   detail::pack(pp, nl, f_pt.data());
   int r_words = 0;
+  if (make_secure && deviceRandoms()) {
+    uint32_t key[8], nonce[3];
+    detail::freshDrbgSeed(key, nonce);
+    DEVICE_CHECK(ipclb200_encrypt_drbg(dev, f_pt.data(), nl, sz, key, nonce, f_ct.data()));
+    return detail::unpack(f_ct.data(), sz, 2 * nl);
+  }
   if (make_secure) flatRandoms(sz, f_r, r_words);
   DEVICE_CHECK(ipclb200_encrypt(dev, f_pt.data(), nl,
                                 make_secure ? f_r.data() : nullptr, r_words, sz,
@@ -243,7 +268,15 @@ CipherText PublicKey::encrypt(const PlainText& pt, bool make_secure) const {
       ipclb200_pubkey* dev = deviceKey();
       std::shared_ptr<detail::DeviceBatch> d_r;
       int r_words = 0;
-      if (make_secure) {
+      if (make_secure && deviceRandoms()) {
+        // fresh DJN randoms never exist on the host: one OS-entropy key per
+        // call, expanded in HBM (drbg.hpp)
+        uint32_t key[8], nonce[3];
+        detail::freshDrbgSeed(key, nonce);
+        r_words = (m_randbits + 31) / 32;
+        d_r = std::make_shared<detail::DeviceBatch>(pt_size, r_words);
+        DEVICE_CHECK(ipclb200_batch_random(d_r->h, m_randbits, key, nonce));
+      } else if (make_secure) {
         std::vector<uint32_t> f_r;
         flatRandoms(pt_size, f_r, r_words);
         d_r = std::make_shared<detail::DeviceBatch>(pt_size, r_words);
