@@ -283,6 +283,13 @@ int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
                           const uint32_t* h_exp_shared, int exp_words, int exp_bits,
                           const uint32_t* h_mod, int mod_words, ipclb200_batch* out);
 
+/* Diagnostics: the lane layout the CRT decrypt picks for a batch of `count`
+ * ciphertexts at p_words-word primes on a device with `sms` SMs (0 = 148):
+ * 0 / 1 / 2 = one (ciphertext, side) task over 2, 4, 8 lanes of a warp (4, 8 at
+ * 64-word primes), -2 = one task per thread.  Host-only (no device needed); the
+ * cost model is fitted to profiles/r02_layout_sweep.jsonl. */
+int ipclb200_decrypt_layout(size_t count, int p_words, int sms);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs the integer-pipe microbenchmark (dependent-carry IMAD.WIDE.U32 chains on
  * every SM) and returns the measured 32x32->64 multiply-accumulate rate; this

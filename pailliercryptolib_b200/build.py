@@ -21,12 +21,11 @@ ORACLE_LIB = os.path.join(ORACLE, "_build", "libpaillier_oracle.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-    "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared",
-    # one translation unit with ~80 kernel instantiations: let the optimiser
-    # work on them in parallel (3 min -> 1.5 min); a fixed split keeps the
-    # generated code independent of the build machine's core count
-    # (measured with this split: 368.5 k pairs/s, unsplit 369.2 k)
-    "--split-compile", "8",
+    "-std=c++17", "-Xcompiler", "-fPIC", "--cudart", "shared",
+    # the main translation unit has ~80 kernel instantiations: --split-compile 8
+    # (CUDA_UNITS) lets the optimiser work on them in parallel (3 min -> 1.5 min);
+    # a fixed split keeps the generated code independent of the build machine's
+    # core count (measured with this split: 368.5 k pairs/s, unsplit 369.2 k)
 ]
 
 
@@ -52,12 +51,20 @@ def _nvcc():
 
 def _cuda_sources():
     srcs = [os.path.join(CSRC, f) for f in
-            ("ipcl_b200.cu", "kernels.cuh", "mont_core.cuh", "mont_hensel.cuh",
-             "host_common.hpp", "hostbn.hpp")]
+            ("ipcl_b200.cu", "hensel_decrypt.cu", "hensel_launch.hpp", "kernels.cuh",
+             "kernels_common.cuh", "kernel_hensel_decrypt.cuh",
+             "mont_core.cuh", "mont_hensel.cuh", "host_common.hpp", "hostbn.hpp")]
     exp = os.path.join(CSRC, "experiments")
     srcs += sorted(os.path.join(exp, f) for f in os.listdir(exp))
     srcs.append(os.path.join(ROOT, "include", "ipcl_b200.h"))
     return srcs
+
+
+# translation units of libipcl_b200.so: (source, extra nvcc flags).  The kernels
+# of the two-digit CRT decrypt are compiled alone and unsplit so that their code
+# does not depend on what else the library contains (csrc/hensel_launch.hpp).
+CUDA_UNITS = (("ipcl_b200.cu", ["--split-compile", "8"]),
+              ("hensel_decrypt.cu", []))
 
 
 def experiments_enabled():
@@ -75,10 +82,26 @@ def build_cuda(force=False, verbose=False):
     if not force and have == want and _newer(CUDA_LIB, srcs):
         return CUDA_LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (
-        ["-DIPCLB200_EXPERIMENTS"] if want == "1" else []) + [
-        "-o", CUDA_LIB, os.path.join(CSRC, "ipcl_b200.cu")]
-    out = _run(cmd)
+    objdir = os.path.join(LIBDIR, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    common = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (
+        ["-DIPCLB200_EXPERIMENTS"] if want == "1" else [])
+    objs, procs = [], []
+    for src, extra in CUDA_UNITS:  # the units compile side by side
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [_nvcc()] + common + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    out = ""
+    for cmd, pr in procs:
+        o, _ = pr.communicate()
+        out += o
+        if pr.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError("build failed: " + " ".join(cmd))
+    _run([_nvcc(), "-shared", "--cudart", "shared", "-gencode",
+          "arch=compute_100a,code=sm_100a", "-o", CUDA_LIB] + objs)
     with open(stamp, "w") as f:
         f.write(want)
     if verbose:

@@ -45,6 +45,7 @@ EXPORTS = [
     "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
     "ipclb200_batch_touch", "ipclb200_privkey_set_schedule",
     "ipclb200_random_dev", "ipclb200_batch_random", "ipclb200_encrypt_drbg",
+    "ipclb200_decrypt_layout",
 ]
 
 
@@ -109,6 +110,11 @@ def shutdown():
 
 def device_count():
     return lib().ipclb200_device_count()
+
+
+def decrypt_layout(count, p_words, sms=0):
+    """lane layout the CRT decrypt picks (host-only diagnostic)"""
+    return int(lib().ipclb200_decrypt_layout(ctypes.c_size_t(count), int(p_words), int(sms)))
 
 
 def launch_count():

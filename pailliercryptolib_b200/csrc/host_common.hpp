@@ -225,34 +225,64 @@ inline void hensel_side_block(const Limbs& p, const Limbs& psq, const Limbs& hp,
   hbn::to_words(nhp, out + (size_t)9 * pl, pl);
 }
 
-// Lane layout of decrypt_hensel_kernel for a batch: spread 0/1/2 = one
-// (ciphertext, side) task over T0, 2*T0, 4*T0 lanes.  A launch is `rounds` of the
-// resident warps; a full round costs F (pipe bound, 12 warps per SM), a partial
-// one max(L, F * fill) -- L = latency of one task alone.  L and F measured at a
-// 2048-bit key (profiles/r02_hensel_small_batches.md), only their ratios matter:
-//   limbs per lane   16: L 10.0  F 20.0     8: L 5.7  F 11.0     4: L 3.95  F 6.5
-// Predicts the measured optimum at every batch size from 16 to 65536.
+// Lane layout of decrypt_hensel_kernel for a batch.  Layouts: 0/1/2 = one
+// (ciphertext, side) task over T0, 2*T0, 4*T0 lanes (fewer limbs per lane: lower
+// latency, more instructions per product), -2 = one task per THREAD (T = 1, only
+// for 32-word primes: fewest instructions, 12 warps per SM, longest latency).
+//
+// A launch is a queue of warp-sized chunks over the 12*sms resident warps.
+// Measured (profiles/r02_layout_sweep.jsonl, 2048-bit key, ms): the time is a
+// staircase in the number of chunks -- `full` complete rounds of the resident
+// warps plus a last round that puts w = 1, 2 or 3 warps on every SM
+// sub-partition:
+//     t = first[w]                                   (no complete round)
+//     t = first[3] + (full - 1) * round + inc[w]     (otherwise)
+// Only the ratios between layouts matter, so the 2048-bit numbers serve every
+// key size.  Layout 2 keeps the simpler max(L, F * fill) model it was fitted
+// with (profiles/r02_hensel_small_batches.md).
+struct HenselStair {
+  double first[3], round, inc[3];
+};
+inline double hensel_stair_time(const HenselStair& m, size_t count, int lanes, int sms) {
+  const size_t per = (size_t)(32 / lanes);
+  const size_t chunks = 2 * ((count + per - 1) / per);
+  const size_t resident = (size_t)12 * (size_t)sms;
+  const size_t full = chunks / resident, rem = chunks % resident;
+  const size_t w = (rem + (size_t)4 * sms - 1) / ((size_t)4 * sms);  // 0..3
+  if (full == 0) return m.first[w ? w - 1 : 0];
+  return m.first[2] + (double)(full - 1) * m.round + (w ? m.inc[w - 1] : 0.0);
+}
 inline int pick_hensel_spread(size_t count, int pl, int sms) {
-  static const double kL[3] = {10.0, 5.7, 3.95}, kF[3] = {20.0, 11.0, 6.5};
+  static const HenselStair kThread = {{17.8, 23.8, 38.65}, 32.6, {8.9, 20.8, 32.6}};
+  static const HenselStair kS0 = {{10.0, 13.67, 21.0}, 20.1, {5.3, 11.5, 19.0}};
+  static const HenselStair kS1 = {{5.72, 8.17, 11.5}, 11.0, {3.9, 6.1, 11.3}};
+  static const double kL2 = 3.95, kF2 = 6.5;
   const int t0 = pl == 64 ? 4 : 2;          // lanes per task at spread 0
-  const int first = pl == 16 ? 1 : 0;       // pl = 16 starts at 8 limbs per lane
   const int nspread = pl == 32 ? 3 : 2;     // instantiated layouts
-  const double resident = 12.0 * sms;       // warps
+  const HenselStair* stairs[2] = {pl == 16 ? &kS1 : &kS0, &kS1};
   int best = 0;
   double best_t = -1;
-  for (int sp = 0; sp < nspread; sp++) {
-    const int T = t0 << sp;
-    const double chunks = 2.0 * (double)((count + (32 / T) - 1) / (32 / T));
-    const double full = (double)(size_t)(chunks / resident);
-    const double fill = chunks / resident - full;
-    const double L = kL[first + sp], F = kF[first + sp];
-    double t = full * F;
-    if (fill > 0) t += (L > F * fill ? L : F * fill);
+  auto consider = [&](int layout, double t) {
     if (best_t < 0 || t < best_t) {
       best_t = t;
-      best = sp;
+      best = layout;
+    }
+  };
+  for (int sp = 0; sp < nspread; sp++) {
+    const int T = t0 << sp;
+    if (sp < 2 && !(pl == 16 && sp == 1)) {
+      consider(sp, hensel_stair_time(*stairs[sp], count, T, sms));
+    } else {
+      const double resident = 12.0 * sms;
+      const double chunks = 2.0 * (double)((count + (32 / T) - 1) / (32 / T));
+      const double full = (double)(size_t)(chunks / resident);
+      const double fill = chunks / resident - full;
+      double t = full * kF2;
+      if (fill > 0) t += (kL2 > kF2 * fill ? kL2 : kF2 * fill);
+      consider(sp, t);
     }
   }
+  if (pl == 32) consider(-2, hensel_stair_time(kThread, count, 1, sms));
   return best;
 }
 

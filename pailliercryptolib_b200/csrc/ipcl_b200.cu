@@ -37,6 +37,7 @@
 #include "host_common.hpp"
 #include "hostbn.hpp"
 #include "kernels.cuh"
+#include "hensel_launch.hpp"
 
 using namespace ipclb200;
 using namespace ipclb200::host;
@@ -1315,28 +1316,10 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
   int want_blocks = 3;
   if (const char* e = getenv("IPCLB200_HENSEL_BLOCKS")) want_blocks = atoi(e);
   if (want_blocks < 1 || want_blocks > 4) want_blocks = 3;
-#define FH(K_, T_, MINB_, ROWS_)                                                        \
-  {                                                                                     \
-    auto kern = decrypt_hensel_kernel<K_, T_, MINB_, ROWS_>;                            \
-    constexpr size_t smem = hensel_smem_bytes<K_, T_>(kBlockThreads);                   \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                  (int)smem));                                          \
-    int per_sm = 0;                                                                     \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, \
-                                                           smem));                      \
-    if (per_sm < 1) return fail(IPCLB200_ERR_CUDA, "hensel kernel does not fit an SM"); \
-    if (per_sm > want_blocks) per_sm = want_blocks;                                     \
-    const size_t gpb = kBlockThreads / T_;                                              \
-    const size_t chunks = 2 * ((count + (32 / T_) - 1) / (32 / T_));                    \
-    const size_t need = (chunks + 3) / 4;                                               \
-    const size_t cap = (size_t)per_sm * op.dev->sms;                                    \
-    const int grid = (int)(need < cap ? need : cap);                                    \
-    TRY(table_ws(op, (size_t)grid * gpb * 2 * pl * p.table_entries, &p.table_ws,        \
-                 &p.work_counter));                                                     \
-    kern<<<grid, kBlockThreads, smem, op.s>>>(p);                                       \
-  }
   int rows = 8;
   if (const char* e = getenv("IPCLB200_HENSEL_ROWS")) rows = atoi(e);
+  bool w64 = false;
+  if (const char* e = getenv("IPCLB200_HENSEL_W64")) w64 = e[0] == '1';
   // Lane layout by batch size: a small batch spreads every (ciphertext, side)
   // task over more lanes (fewer limbs per lane) so that the launch fills the
   // GPU and a task's latency shrinks -- the idea of the wide layouts of the
@@ -1349,28 +1332,19 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
     if (w && w[0] == '1') spread = 2;
     if (w && w[0] == '2') spread = 1;
   }
-  switch (pl) {
-    case 16:
-      if (spread >= 1) FH(4, 4, 3, 8) else FH(8, 2, 3, 8)
-      break;
-    case 32:
-      if (spread >= 2) FH(4, 8, 3, 8)
-      else if (spread == 1) FH(8, 4, 3, 8)
-      else if (spread == -1 && rows == 4) FH(32, 1, 2, 4)
-      else if (spread == -1) FH(32, 1, 2, 8)
-      else if (rows == 4) FH(16, 2, 3, 4)
-      else if (rows == 16) FH(16, 2, 3, 16)
-      else FH(16, 2, 3, 8)
-      break;
-    case 48:
-      if (spread >= 1) FH(12, 4, 3, 8) else FH(24, 2, 2, 8)
-      break;
-    case 64:
-      if (spread >= 1) FH(8, 8, 3, 8) else FH(16, 4, 3, 8)
-      break;
-    default: return fail(IPCLB200_ERR_UNSUPPORTED, "hensel: unsupported prime width");
+  // the kernels live in hensel_decrypt.cu (a translation unit of their own)
+  HenselDecryptPlan plan;
+  {
+    const cudaError_t e =
+        hensel_decrypt_plan(pl, spread, rows, w64, count, op.dev->sms, want_blocks, &plan);
+    if (e == cudaErrorInvalidValue)
+      return fail(IPCLB200_ERR_UNSUPPORTED, "hensel: unsupported prime width");
+    if (e == cudaErrorLaunchOutOfResources)
+      return fail(IPCLB200_ERR_CUDA, "hensel kernel does not fit an SM");
+    CUDA_TRY(e);
   }
-#undef FH
+  TRY(table_ws(op, plan.groups * 2 * pl * p.table_entries, &p.table_ws, &p.work_counter));
+  plan.launch(p, plan.grid, plan.smem, op.s);
   g.launches++;
   CUDA_TRY(cudaGetLastError());
   CrtCombineParams f{};
@@ -2735,6 +2709,10 @@ int ipclb200_modexp_batch(const ipclb200_batch* base, const ipclb200_batch* exp,
 }
 
 // ---- measurement ----------------------------------------------------------
+int ipclb200_decrypt_layout(size_t count, int p_words, int sms) {
+  return pick_hensel_spread(count, p_words, sms > 0 ? sms : 148);
+}
+
 int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz) {
   Dev* dev = nullptr;
   TRY(primary_device(&dev));

@@ -79,6 +79,60 @@ __device__ __forceinline__ void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b,
                : "r"(a), "r"(b), "r"(c));
 }
 
+// ---- the same products on 64-bit accumulator words: the halves of one 64-bit
+// PTX register are a register pair from the start, which lets ptxas keep the
+// loop-carried accumulators in place across a rolled loop (with 32-bit halves it
+// pairs them late and re-shuffles ~50 registers per iteration) -----------------
+__device__ __forceinline__ uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+__device__ __forceinline__ uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+// d = a*b + c, carry out (first of a chain)
+__device__ __forceinline__ void mad_wide_cc(uint64_t& d, uint32_t a, uint32_t b, uint64_t c) {
+  asm volatile(
+      "{\n\t.reg .u32 cl, ch, dl, dh;\n\t"
+      "mov.b64 {cl, ch}, %3;\n\t"
+      "mad.lo.cc.u32 dl, %1, %2, cl;\n\t"
+      "madc.hi.cc.u32 dh, %1, %2, ch;\n\t"
+      "mov.b64 %0, {dl, dh};\n\t}"
+      : "=l"(d)
+      : "r"(a), "r"(b), "l"(c));
+}
+// d = a*b + c + carry in, carry out
+__device__ __forceinline__ void madc_wide_cc(uint64_t& d, uint32_t a, uint32_t b, uint64_t c) {
+  asm volatile(
+      "{\n\t.reg .u32 cl, ch, dl, dh;\n\t"
+      "mov.b64 {cl, ch}, %3;\n\t"
+      "madc.lo.cc.u32 dl, %1, %2, cl;\n\t"
+      "madc.hi.cc.u32 dh, %1, %2, ch;\n\t"
+      "mov.b64 %0, {dl, dh};\n\t}"
+      : "=l"(d)
+      : "r"(a), "r"(b), "l"(c));
+}
+// lo half += x with carry out, hi half unchanged
+__device__ __forceinline__ void add_lo_cc(uint64_t& d, uint64_t c, uint32_t x) {
+  asm volatile(
+      "{\n\t.reg .u32 cl, ch, dl;\n\t"
+      "mov.b64 {cl, ch}, %1;\n\t"
+      "add.cc.u32 dl, cl, %2;\n\t"
+      "mov.b64 %0, {dl, ch};\n\t}"
+      : "=l"(d)
+      : "l"(c), "r"(x));
+}
+// {lo, hi} = {a + b, carry}
+__device__ __forceinline__ void add_wide(uint64_t& d, uint32_t a, uint32_t b) {
+  asm volatile(
+      "{\n\t.reg .u32 dl, dh;\n\t"
+      "add.cc.u32 dl, %1, %2;\n\t"
+      "addc.u32 dh, 0, 0;\n\t"
+      "mov.b64 %0, {dl, dh};\n\t}"
+      : "=l"(d)
+      : "r"(a), "r"(b));
+}
+
 // Everything below is parameterised on K (limbs per lane, even) and T (lanes
 // per big integer, power of two <= 32).
 template <int K, int T>

@@ -76,17 +76,23 @@ __device__ __forceinline__ void fence_async_proxy() {
 // ptxas needs ~30 register moves per iteration to bring the two accumulator
 // arrays back to their registers, so fewer iterations are cheaper -- until the
 // hot loop outgrows the instruction cache.
-template <int K, int T, int ROWS = 8>
+template <int K, int T, int ROWS = 8, bool W64 = false, bool COMPACT = false>
 struct HMont {
   using M = Mont<K, T>;
   static constexpr int LH = K * T;
   static_assert(ROWS % 4 == 0 && LH % ROWS == 0, "ROWS must divide LH");
-  // per-group shared-memory area (words)
+  // per-group shared-memory area (words).  COMPACT: no separate buffer for the
+  // table entry of the next multiply -- it is fetched into S0|S1 when the multiply
+  // starts (a squaring's staging areas, dead by then) and digit 0 of a result is
+  // parked in its own area P: 4*LH + 4 words per task instead of 5*LH + 4, which
+  // is what lets the thread-per-task layout keep 12 warps on an SM.
   static constexpr int kS0 = 0;         // pass A multiplier of a squaring (x0)
   static constexpr int kS1 = LH;        // pass B multiplier of a squaring (2w mod R)
   static constexpr int kSQ = 2 * LH;    // quotient digits of pass A
-  static constexpr int kT0 = 3 * LH;    // table entry: y0 | wy
-  static constexpr int kStride = 5 * LH + 4;  // 16-byte multiple, 4-word bank skew per group
+  static constexpr int kT0 = COMPACT ? 0 : 3 * LH;  // table entry: y0 | wy
+  static constexpr int kP = COMPACT ? 3 * LH : 0;   // digit 0 parked during pass B
+  // 16-byte multiple, 4-word bank skew per group
+  static constexpr int kStride = (COMPACT ? 4 : 5) * LH + 4;
 
   __device__ __forceinline__ static int lane_t() { return M::lane_t(); }
 
@@ -172,6 +178,67 @@ struct HMont {
     return (lane_t() == T - 1) ? 0u : down;
   }
 
+  // ---- the same row on 64-bit accumulator words (W64): array A of K limbs + 1
+  // overflow limb = K/2 words w[u] = {A[2u], A[2u+1]} and top = A[K].  In the
+  // odd role the array moves down one word per row (w[u] <- w[u+1]), hi(w[0]) is
+  // the stranded half that belongs to limb 0.
+  template <int MODE>
+  __device__ __forceinline__ static uint32_t row64(
+      uint64_t (&P)[K / 2], uint32_t& Pt, uint64_t (&Q)[K / 2], uint32_t& Qt,
+      const uint32_t (&a)[K], const uint32_t (&a2)[K], const uint32_t (&n)[K], uint32_t b,
+      uint32_t b2, uint32_t mi, uint32_t in_limb, uint32_t n0inv, uint32_t& qout) {
+    uint64_t t;
+    add_wide(t, Qt, in_limb);
+    add_lo_cc(P[0], P[0], hi32(Q[0]));
+#pragma unroll
+    for (int u = 0; u < K / 2 - 1; u++) madc_wide_cc(Q[u], a[2 * u + 1], b, Q[u + 1]);
+    madc_wide_cc(Q[K / 2 - 1], a[K - 1], b, t);
+    addc(Qt, 0, 0);
+    mad_wide_cc(P[0], a[0], b, P[0]);
+#pragma unroll
+    for (int u = 1; u < K / 2; u++) madc_wide_cc(P[u], a[2 * u], b, P[u]);
+    addc(Pt, Pt, 0);
+    if (MODE == 2) {
+      mad_wide_cc(P[0], a2[0], b2, P[0]);
+#pragma unroll
+      for (int u = 1; u < K / 2; u++) madc_wide_cc(P[u], a2[2 * u], b2, P[u]);
+      addc(Pt, Pt, 0);
+      mad_wide_cc(Q[0], a2[1], b2, Q[0]);
+#pragma unroll
+      for (int u = 1; u < K / 2; u++) madc_wide_cc(Q[u], a2[2 * u + 1], b2, Q[u]);
+      addc(Qt, Qt, 0);
+    }
+    uint32_t q = (MODE == 0 ? lo32(P[0]) : lo32(P[0]) + mi) * n0inv;
+    if (T > 1) q = __shfl_sync(IPCLB200_FULL_MASK, q, 0, T);
+    qout = q;
+    mad_wide_cc(P[0], n[0], q, P[0]);
+#pragma unroll
+    for (int u = 1; u < K / 2; u++) madc_wide_cc(P[u], n[2 * u], q, P[u]);
+    addc(Pt, Pt, 0);
+    if (MODE == 0) {
+      mad_wide_cc(Q[0], n[1], q, Q[0]);
+    } else {
+      uint32_t scratch;
+      add_cc(scratch, mi ? 1u : 0u, 0xffffffffu);  // CF = [mi != 0]
+      madc_wide_cc(Q[0], n[1], q, Q[0]);
+    }
+#pragma unroll
+    for (int u = 1; u < K / 2; u++) madc_wide_cc(Q[u], n[2 * u + 1], q, Q[u]);
+    addc(Qt, Qt, 0);
+    if (T == 1) return 0u;
+    uint32_t down = __shfl_down_sync(IPCLB200_FULL_MASK, lo32(P[0]), 1, T);
+    return (lane_t() == T - 1) ? 0u : down;
+  }
+  __device__ __forceinline__ static void unpack64(uint32_t (&A)[K + 1], const uint64_t (&w)[K / 2],
+                                                  uint32_t top) {
+#pragma unroll
+    for (int u = 0; u < K / 2; u++) {
+      A[2 * u] = lo32(w[u]);
+      A[2 * u + 1] = hi32(w[u]);
+    }
+    A[K] = top;
+  }
+
   // E (even role) + O (odd role, one-word shift pending) + the top word (t0,t1)
   // -> K limbs per lane with the cross-lane carries resolved.  Returns how many
   // times R the value overflows (group-uniform).
@@ -198,28 +265,24 @@ struct HMont {
 
   // value = r + c*R - dec  ->  r in [0, R) by subtracting multiples of n.
   // c, dec group-uniform.  Returns the number of subtractions (group-uniform).
-  // Round 1 takes the decrement along: r + ~n + (1 - dec), or r + ~0 if there is
-  // nothing to subtract; each participating round leaves c - 1 + carry.
+  // The first round takes the decrement along: r + ~n + (1 - dec), or r + ~0 if
+  // there is nothing to subtract; each participating round leaves c - 1 + carry.
+  // ONE copy of the add chain (the hot loop has to stay in the instruction cache).
   __device__ __forceinline__ static uint32_t reduce(uint32_t (&r)[K], uint32_t c,
                                                     uint32_t dec,
                                                     const uint32_t (&n)[K]) {
     uint32_t subs = 0;
-    if (__any_sync(IPCLB200_FULL_MASK, (c | dec) != 0)) {
-      uint32_t y[K];
-#pragma unroll
-      for (int j = 0; j < K; j++) y[j] = c ? ~n[j] : (dec ? 0xffffffffu : 0u);
-      const uint32_t carry = M::group_add(r, y, (c && !dec) ? 1u : 0u);
-      subs = c ? 1u : 0u;
-      c = (c | dec) ? c - 1u + carry : c;
-    }
 #pragma unroll 1
-    while (__any_sync(IPCLB200_FULL_MASK, c != 0)) {
+    while (__any_sync(IPCLB200_FULL_MASK, (c | dec) != 0)) {
+      const uint32_t mc = c ? 0xffffffffu : 0u;           // subtract n
+      const uint32_t md = (!c && dec) ? 0xffffffffu : 0u;  // only the decrement
       uint32_t y[K];
 #pragma unroll
-      for (int j = 0; j < K; j++) y[j] = c ? ~n[j] : 0u;
-      const uint32_t carry = M::group_add(r, y, c ? 1u : 0u);
+      for (int j = 0; j < K; j++) y[j] = (~n[j] & mc) | md;
+      const uint32_t carry = M::group_add(r, y, (c && !dec) ? 1u : 0u);
       subs += c ? 1u : 0u;
-      c = c ? c - 1u + carry : 0u;
+      c = (c | dec) ? c - 1u + carry : c;
+      dec = 0;
     }
     return subs;
   }
@@ -231,33 +294,66 @@ struct HMont {
                                                     const uint32_t* bs, uint32_t* qs,
                                                     const uint32_t (&n)[K],
                                                     uint32_t n0inv) {
-    uint32_t E[K + 1], O[K + 1];
-#pragma unroll
-    for (int j = 0; j <= K; j++) {
-      E[j] = 0;
-      O[j] = 0;
-    }
-    uint32_t in_limb = 0;
-    const bool l0 = lane_t() == 0;
-#pragma unroll 1
-    for (int i = 0; i < LH; i += ROWS) {
-#pragma unroll
-      for (int k = 0; k < ROWS; k += 4) {
-        const uint4 bv = *reinterpret_cast<const uint4*>(bs + i + k);
-        uint4 qv;
-        in_limb = row<0>(E, O, a, a, n, bv.x, 0u, 0u, in_limb, n0inv, qv.x);
-        in_limb = row<0>(O, E, a, a, n, bv.y, 0u, 0u, in_limb, n0inv, qv.y);
-        in_limb = row<0>(E, O, a, a, n, bv.z, 0u, 0u, in_limb, n0inv, qv.z);
-        in_limb = row<0>(O, E, a, a, n, bv.w, 0u, 0u, in_limb, n0inv, qv.w);
-        if (l0) *reinterpret_cast<uint4*>(qs + i + k) = qv;
-      }
-    }
-    uint32_t t0, t1;
-    add_cc(t0, O[K], in_limb);
-    addc(t1, 0, 0);
+    uint32_t E[K + 1], O[K + 1], t0, t1;
+    sweep_a(E, O, t0, t1, a, bs, qs, n, n0inv);
     const uint32_t c = assemble(r, E, O, t0, t1);
     reduce(r, c, 0u, n);
     return c;
+  }
+  // the rows of pass A: leaves the accumulator arrays and the top word (t0,t1)
+  __device__ __forceinline__ static void sweep_a(uint32_t (&E)[K + 1], uint32_t (&O)[K + 1],
+                                                 uint32_t& t0, uint32_t& t1,
+                                                 const uint32_t (&a)[K],
+                                                 const uint32_t* bs, uint32_t* qs,
+                                                 const uint32_t (&n)[K],
+                                                 uint32_t n0inv) {
+    uint32_t in_limb = 0;
+    const bool l0 = lane_t() == 0;
+    if (W64) {
+      uint64_t Ew[K / 2], Ow[K / 2];
+      uint32_t Et = 0, Ot = 0;
+#pragma unroll
+      for (int u = 0; u < K / 2; u++) {
+        Ew[u] = 0;
+        Ow[u] = 0;
+      }
+#pragma unroll 1
+      for (int i = 0; i < LH; i += ROWS) {
+#pragma unroll
+        for (int k = 0; k < ROWS; k += 4) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(bs + i + k);
+          uint4 qv;
+          in_limb = row64<0>(Ew, Et, Ow, Ot, a, a, n, bv.x, 0u, 0u, in_limb, n0inv, qv.x);
+          in_limb = row64<0>(Ow, Ot, Ew, Et, a, a, n, bv.y, 0u, 0u, in_limb, n0inv, qv.y);
+          in_limb = row64<0>(Ew, Et, Ow, Ot, a, a, n, bv.z, 0u, 0u, in_limb, n0inv, qv.z);
+          in_limb = row64<0>(Ow, Ot, Ew, Et, a, a, n, bv.w, 0u, 0u, in_limb, n0inv, qv.w);
+          if (l0) *reinterpret_cast<uint4*>(qs + i + k) = qv;
+        }
+      }
+      unpack64(E, Ew, Et);
+      unpack64(O, Ow, Ot);
+    } else {
+#pragma unroll
+      for (int j = 0; j <= K; j++) {
+        E[j] = 0;
+        O[j] = 0;
+      }
+#pragma unroll 1
+      for (int i = 0; i < LH; i += ROWS) {
+#pragma unroll
+        for (int k = 0; k < ROWS; k += 4) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(bs + i + k);
+          uint4 qv;
+          in_limb = row<0>(E, O, a, a, n, bv.x, 0u, 0u, in_limb, n0inv, qv.x);
+          in_limb = row<0>(O, E, a, a, n, bv.y, 0u, 0u, in_limb, n0inv, qv.y);
+          in_limb = row<0>(E, O, a, a, n, bv.z, 0u, 0u, in_limb, n0inv, qv.z);
+          in_limb = row<0>(O, E, a, a, n, bv.w, 0u, 0u, in_limb, n0inv, qv.w);
+          if (l0) *reinterpret_cast<uint4*>(qs + i + k) = qv;
+        }
+      }
+    }
+    add_cc(t0, O[K], in_limb);
+    addc(t1, 0, 0);
   }
 
   // ---- pass B: r = (a*B1 [+ a2*B0] + m) / R [+ hb*a] - dec mod n (r < R) -------
@@ -269,57 +365,94 @@ struct HMont {
       uint32_t (&r)[K], const uint32_t (&a)[K], const uint32_t (&a2)[K],
       const uint32_t* b1s, const uint32_t* b0s, const uint32_t* qs,
       const uint32_t (&n)[K], uint32_t n0inv, uint32_t hb, uint32_t dec) {
-    uint32_t E[K + 1], O[K + 1];
-#pragma unroll
-    for (int j = 0; j <= K; j++) {
-      E[j] = 0;
-      O[j] = 0;
-    }
-    uint32_t in_limb = 0, qd;
-    const bool l0 = lane_t() == 0;
-    __syncwarp();  // qs was written by lane 0 of the group
-#pragma unroll 1
-    for (int i = 0; i < LH; i += ROWS) {
-#pragma unroll
-      for (int k = 0; k < ROWS; k += 4) {
-        const uint4 bv = *reinterpret_cast<const uint4*>(b1s + i + k);
-        uint4 cv = make_uint4(0, 0, 0, 0);
-        if (TWO) cv = *reinterpret_cast<const uint4*>(b0s + i + k);
-        uint4 mv = *reinterpret_cast<const uint4*>(qs + i + k);
-        if (!l0) mv = make_uint4(0, 0, 0, 0);
-        constexpr int MD = TWO ? 2 : 1;
-        in_limb = row<MD>(E, O, a, a2, n, bv.x, cv.x, mv.x, in_limb, n0inv, qd);
-        in_limb = row<MD>(O, E, a, a2, n, bv.y, cv.y, mv.y, in_limb, n0inv, qd);
-        in_limb = row<MD>(E, O, a, a2, n, bv.z, cv.z, mv.z, in_limb, n0inv, qd);
-        in_limb = row<MD>(O, E, a, a2, n, bv.w, cv.w, mv.w, in_limb, n0inv, qd);
-      }
-    }
-    uint32_t t0, t1;
-    add_cc(t0, O[K], in_limb);
-    addc(t1, 0, 0);
-    if (!TWO) {
-      // half row: E,O += a * hb (no quotient, no shift).  Odd word u of O lives
-      // in O[2u+2..2u+3], the top one in (t0,t1).
-      mad_lo_cc(O[2], a[1], hb, O[2]);
-      madc_hi_cc(O[3], a[1], hb, O[3]);
-#pragma unroll
-      for (int u = 1; u < K / 2 - 1; u++) {
-        madc_lo_cc(O[2 * u + 2], a[2 * u + 1], hb, O[2 * u + 2]);
-        madc_hi_cc(O[2 * u + 3], a[2 * u + 1], hb, O[2 * u + 3]);
-      }
-      madc_lo_cc(t0, a[K - 1], hb, t0);
-      madc_hi_cc(t1, a[K - 1], hb, t1);
-      mad_lo_cc(E[0], a[0], hb, E[0]);
-      madc_hi_cc(E[1], a[0], hb, E[1]);
-#pragma unroll
-      for (int u = 1; u < K / 2; u++) {
-        madc_lo_cc(E[2 * u], a[2 * u], hb, E[2 * u]);
-        madc_hi_cc(E[2 * u + 1], a[2 * u], hb, E[2 * u + 1]);
-      }
-      addc(E[K], E[K], 0);
-    }
+    uint32_t E[K + 1], O[K + 1], t0, t1;
+    sweep_b<TWO>(E, O, t0, t1, a, a2, b1s, b0s, qs, n, n0inv, hb);
     const uint32_t c = assemble(r, E, O, t0, t1);
     reduce(r, c, dec, n);
+  }
+  template <bool TWO>
+  __device__ __forceinline__ static void sweep_b(
+      uint32_t (&E)[K + 1], uint32_t (&O)[K + 1], uint32_t& t0, uint32_t& t1,
+      const uint32_t (&a)[K], const uint32_t (&a2)[K], const uint32_t* b1s,
+      const uint32_t* b0s, const uint32_t* qs, const uint32_t (&n)[K], uint32_t n0inv,
+      uint32_t hb) {
+    uint32_t in_limb = 0, qd;
+    const bool l0 = lane_t() == 0;
+    constexpr int MD = TWO ? 2 : 1;
+    __syncwarp();  // qs was written by lane 0 of the group
+    if (W64) {
+      uint64_t Ew[K / 2], Ow[K / 2];
+      uint32_t Et = 0, Ot = 0;
+#pragma unroll
+      for (int u = 0; u < K / 2; u++) {
+        Ew[u] = 0;
+        Ow[u] = 0;
+      }
+#pragma unroll 1
+      for (int i = 0; i < LH; i += ROWS) {
+#pragma unroll
+        for (int k = 0; k < ROWS; k += 4) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(b1s + i + k);
+          uint4 cv = make_uint4(0, 0, 0, 0);
+          if (TWO) cv = *reinterpret_cast<const uint4*>(b0s + i + k);
+          uint4 mv = *reinterpret_cast<const uint4*>(qs + i + k);
+          if (!l0) mv = make_uint4(0, 0, 0, 0);
+          in_limb = row64<MD>(Ew, Et, Ow, Ot, a, a2, n, bv.x, cv.x, mv.x, in_limb, n0inv, qd);
+          in_limb = row64<MD>(Ow, Ot, Ew, Et, a, a2, n, bv.y, cv.y, mv.y, in_limb, n0inv, qd);
+          in_limb = row64<MD>(Ew, Et, Ow, Ot, a, a2, n, bv.z, cv.z, mv.z, in_limb, n0inv, qd);
+          in_limb = row64<MD>(Ow, Ot, Ew, Et, a, a2, n, bv.w, cv.w, mv.w, in_limb, n0inv, qd);
+        }
+      }
+      unpack64(E, Ew, Et);
+      unpack64(O, Ow, Ot);
+    } else {
+#pragma unroll
+      for (int j = 0; j <= K; j++) {
+        E[j] = 0;
+        O[j] = 0;
+      }
+#pragma unroll 1
+      for (int i = 0; i < LH; i += ROWS) {
+#pragma unroll
+        for (int k = 0; k < ROWS; k += 4) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(b1s + i + k);
+          uint4 cv = make_uint4(0, 0, 0, 0);
+          if (TWO) cv = *reinterpret_cast<const uint4*>(b0s + i + k);
+          uint4 mv = *reinterpret_cast<const uint4*>(qs + i + k);
+          if (!l0) mv = make_uint4(0, 0, 0, 0);
+          in_limb = row<MD>(E, O, a, a2, n, bv.x, cv.x, mv.x, in_limb, n0inv, qd);
+          in_limb = row<MD>(O, E, a, a2, n, bv.y, cv.y, mv.y, in_limb, n0inv, qd);
+          in_limb = row<MD>(E, O, a, a2, n, bv.z, cv.z, mv.z, in_limb, n0inv, qd);
+          in_limb = row<MD>(O, E, a, a2, n, bv.w, cv.w, mv.w, in_limb, n0inv, qd);
+        }
+      }
+    }
+    add_cc(t0, O[K], in_limb);
+    addc(t1, 0, 0);
+    if (!TWO) half_row(E, O, t0, t1, a, hb);
+  }
+  // half row: E,O += a * hb (no quotient, no shift).  Odd word u of O lives in
+  // O[2u+2..2u+3], the top one in (t0,t1).
+  __device__ __forceinline__ static void half_row(uint32_t (&E)[K + 1], uint32_t (&O)[K + 1],
+                                                  uint32_t& t0, uint32_t& t1,
+                                                  const uint32_t (&a)[K], uint32_t hb) {
+    mad_lo_cc(O[2], a[1], hb, O[2]);
+    madc_hi_cc(O[3], a[1], hb, O[3]);
+#pragma unroll
+    for (int u = 1; u < K / 2 - 1; u++) {
+      madc_lo_cc(O[2 * u + 2], a[2 * u + 1], hb, O[2 * u + 2]);
+      madc_hi_cc(O[2 * u + 3], a[2 * u + 1], hb, O[2 * u + 3]);
+    }
+    madc_lo_cc(t0, a[K - 1], hb, t0);
+    madc_hi_cc(t1, a[K - 1], hb, t1);
+    mad_lo_cc(E[0], a[0], hb, E[0]);
+    madc_hi_cc(E[1], a[0], hb, E[1]);
+#pragma unroll
+    for (int u = 1; u < K / 2; u++) {
+      madc_lo_cc(E[2 * u], a[2 * u], hb, E[2 * u]);
+      madc_hi_cc(E[2 * u + 1], a[2 * u], hb, E[2 * u + 1]);
+    }
+    addc(E[K], E[K], 0);
   }
 
   // this lane's K limbs -> the group's LH-word shared operand
@@ -407,11 +540,11 @@ struct HMont {
     {
       // digit 0 of the result waits in this lane's slice of S0 (dead after pass A:
       // a squaring has consumed its copy of x0, a multiply reads the entry buffer)
-      // while pass B runs: 16 registers less in the hottest loop
+      // while pass B runs: K registers less in the hottest loop
       uint32_t z0[K];
       ovA = pass_a(z0, x0, is_mul ? ys : sm + kS0, sm + kSQ, n, n0inv);
       __syncwarp();  // every lane of the group is done reading S0
-      put(sm + kS0, z0);
+      put(sm + kP, z0);
     }
     if (is_mul) {
       uint32_t wz[K];
@@ -421,7 +554,7 @@ struct HMont {
     } else {
       pass_b<false>(w, x0, x0, sm + kS1, sm + kS1, sm + kSQ, n, n0inv, hb, ovA);
     }
-    M::load(x0, sm + kS0);  // this lane's own slice: no synchronisation needed
+    M::load(x0, sm + kP);  // this lane's own slice: no synchronisation needed
   }
 
   // ---- (x0, w) <- (a, 0) * (k0, kw), the constant pair already staged at

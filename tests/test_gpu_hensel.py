@@ -95,6 +95,29 @@ def test_hensel_row_unroll_variants(capi, all_keys, rows, monkeypatch):
     assert batch_from_limbs(base[:4]) == [dec_crt(p, q, c) for c in cts[:4]]
 
 
+@pytest.mark.parametrize("name", ["2048", "2048_low", "2048_high"])
+@pytest.mark.parametrize("layout", ["-2", "-1", "0", "1", "2"])
+def test_hensel_layouts_agree_with_pow(capi, all_keys, name, layout, monkeypatch):
+    """every lane layout of the two-digit decrypt at 32-word primes -- one task
+    per thread (-2: compact staging, 12 warps per SM; -1: with the prefetch
+    buffer), per 2, 4, 8 lanes -- on edge ciphertexts, a ragged count that leaves
+    lanes of the last warp idle, constant schedule included"""
+    k = all_keys[name]
+    p, q = sorted((k["p"], k["q"]))
+    rng = np.random.default_rng(sum(map(ord, name)) + 7)
+    count = 333
+    cts, words = _ciphertexts(rng, p, q, count)
+    ct = batch_to_limbs(cts, words)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    monkeypatch.delenv("IPCLB200_DECRYPT", raising=False)
+    monkeypatch.setenv("IPCLB200_HENSEL_SPREAD", layout)
+    monkeypatch.setenv("IPCLB200_HENSEL_W64", "1")
+    got = batch_from_limbs(sk.decrypt(ct))
+    assert got == [dec_crt(p, q, c) for c in cts]
+    sk.set_schedule(True)
+    assert batch_from_limbs(sk.decrypt(ct)) == got
+
+
 def test_full_batch_65536_bit_exact_vs_oracle(capi, oracle, keys):
     """BASELINE.json configs[1] at full size, every element compared bit for bit
     with the oracle (AVX512-IFMA mb8 restatement, itself pinned to the ISO KAT

@@ -36,12 +36,11 @@ def main():
         d_ct = torch.from_numpy(ct.view(np.int32)).cuda()
         d_pt = torch.zeros((count, NL), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
-        configs = [{}, {"IPCLB200_HENSEL_SPREAD": "-1", "IPCLB200_HENSEL_ROWS": "4"},
-                   {"IPCLB200_HENSEL_SPREAD": "-1", "IPCLB200_HENSEL_ROWS": "8"},
-                   {"IPCLB200_HENSEL_SPREAD": "-1", "IPCLB200_HENSEL_ROWS": "4",
-                    "IPCLB200_HENSEL_BLOCKS": "1"}]
+        configs = [{"IPCLB200_HENSEL_SPREAD": "0"}, {"IPCLB200_HENSEL_SPREAD": "1"},
+                   {"IPCLB200_HENSEL_SPREAD": "-2"}]
         for env in configs:
-            for a in ("IPCLB200_HENSEL_ROWS", "IPCLB200_HENSEL_BLOCKS", "IPCLB200_HENSEL_SPREAD"):
+            for a in ("IPCLB200_HENSEL_ROWS", "IPCLB200_HENSEL_BLOCKS", "IPCLB200_HENSEL_SPREAD",
+                      "IPCLB200_HENSEL_W64"):
                 os.environ.pop(a, None)
             os.environ.update(env)
             with torch.cuda.stream(stream):
@@ -52,7 +51,7 @@ def main():
                 ok = bool(np.array_equal(d_pt.cpu().numpy().view(np.uint32), pt))
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                reps = 5
+                reps = 3
                 for _ in range(reps):
                     sk.decrypt_dev(d_ct.data_ptr(), count, d_pt.data_ptr(), stream.cuda_stream)
                 b.record(stream)
