@@ -708,8 +708,9 @@ def main():
         ach = B * MAC_DECRYPT / dec_s / 1e12
         exec_macs = hensel_executed_macs(p, q)
         roofline = {
-            "kernel": "decrypt_hensel_kernel<16,2> + crt_combine_kernel (per ciphertext two "
-                      "1024-bit-exponent modexps mod p^2, q^2 in two-digit arithmetic)",
+            "kernel": "decrypt_hensel_kernel<32,1,3,4,W64,128,compact> + crt_combine_kernel "
+                      "(per ciphertext two 1024-bit-exponent modexps mod p^2, q^2 in two-digit "
+                      "arithmetic, one (ciphertext, side) task per thread, 12 warps/SM)",
             "bound": "int32_alu",
             "achieved": ach, "peak": peak_mac / 1e12, "unit": "TMAC32/s",
             "frac": ach / (peak_mac / 1e12),
@@ -729,6 +730,7 @@ def main():
             "traffic_source": (traffic or {}).get(
                 "source", "none") + " (static: read from profiles/ncu_traffic.json, "
                                     "not measured in this run)",
+            "traffic_note": (traffic or {}).get("note"),
             "hbm": {"achieved": B * BYTES_DECRYPT / dec_s / 1e9, "peak": hbm_peak,
                     "unit": "GB/s",
                     "frac": B * BYTES_DECRYPT / dec_s / 1e9 / hbm_peak,

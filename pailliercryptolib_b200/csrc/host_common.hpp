@@ -283,6 +283,12 @@ inline int pick_hensel_spread(size_t count, int pl, int sms) {
     }
   }
   if (pl == 32) consider(-2, hensel_stair_time(kThread, count, 1, sms));
+  // 48-word primes (3072-bit keys): layout 0 is 24 limbs x 2 lanes at 252
+  // registers, i.e. 8 warps per SM, and runs latency-bound once a launch is more
+  // than one round of those warps; the 12 x 4 layout keeps 12 warps per SM
+  // (profiles/r02_layout_other_keys.jsonl: 8192 ciphertexts 42.9 vs 45.7 ms,
+  // 32768: 173 vs 152 ms, 65536: 311 vs 301 ms)
+  if (pl == 48 && best == 0 && 2 * ((count + 15) / 16) > (size_t)8 * (size_t)sms) best = 1;
   return best;
 }
 

@@ -44,3 +44,7 @@ def test_headline_batch_runs_one_task_per_thread():
     for pl in (16, 48, 64):
         for count in (8, 1000, 65536):
             assert capi.decrypt_layout(count, pl, 148) in (0, 1)
+    # 3072-bit keys: 24 x 2 lanes (8 warps/SM) only while the launch is one round
+    assert capi.decrypt_layout(8192, 48, 148) == 0
+    assert capi.decrypt_layout(32768, 48, 148) == 1
+    assert capi.decrypt_layout(262144, 48, 148) == 1

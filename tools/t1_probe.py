@@ -36,8 +36,8 @@ def main():
         d_ct = torch.from_numpy(ct.view(np.int32)).cuda()
         d_pt = torch.zeros((count, NL), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
-        configs = [{"IPCLB200_HENSEL_SPREAD": "0"}, {"IPCLB200_HENSEL_SPREAD": "1"},
-                   {"IPCLB200_HENSEL_SPREAD": "-2"}]
+        configs = [{"IPCLB200_HENSEL_SPREAD": v} for v in
+                   os.environ.get("PROBE_LAYOUTS", "0,1,-2").split(",")]
         for env in configs:
             for a in ("IPCLB200_HENSEL_ROWS", "IPCLB200_HENSEL_BLOCKS", "IPCLB200_HENSEL_SPREAD",
                       "IPCLB200_HENSEL_W64"):
