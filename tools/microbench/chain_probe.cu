@@ -19,7 +19,9 @@ __device__ __forceinline__ void madc_wide_cc(uint64_t& d, uint32_t a, uint32_t b
 }
 
 template <int C, int LEN>
-__global__ void __launch_bounds__(128) chains(uint32_t* out, uint32_t a, uint32_t b, int iters) {
+__global__ void __launch_bounds__(128) chains(uint32_t* out, uint32_t a, uint32_t b, int iters,
+                                              unsigned long long* cyc) {
+  const long long c0 = clock64();
   uint64_t acc[C][LEN];
   uint32_t sink[C];
 #pragma unroll
@@ -47,24 +49,29 @@ __global__ void __launch_bounds__(128) chains(uint32_t* out, uint32_t a, uint32_
     for (int j = 0; j < LEN; j++) s ^= (uint32_t)acc[c][j] ^ (uint32_t)(acc[c][j] >> 32);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  // SM cycles this warp was running (clock64 counts at the SM clock)
+  if ((threadIdx.x & 31) == 0) atomicMax(cyc, (unsigned long long)(clock64() - c0));
 }
 
 template <int C, int LEN>
-void run(int warps_per_sm, uint32_t* d, int sms, double ghz) {
+void run(int warps_per_sm, uint32_t* d, int sms, unsigned long long* d_cyc) {
   const int iters = 20000 / (C * LEN) * 8;
   const int blocks = sms * warps_per_sm / 4;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  chains<C, LEN><<<blocks, 128>>>(d, 3, 5, iters);
+  chains<C, LEN><<<blocks, 128>>>(d, 3, 5, iters, d_cyc);
+  cudaMemset(d_cyc, 0, 8);
   cudaEventRecord(e0);
-  chains<C, LEN><<<blocks, 128>>>(d, 3, 5, iters);
+  chains<C, LEN><<<blocks, 128>>>(d, 3, 5, iters, d_cyc);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
+  unsigned long long cycles = 0;
+  cudaMemcpy(&cycles, d_cyc, 8, cudaMemcpyDeviceToHost);
   const double wide = (double)iters * C * LEN;              // per warp
-  const double cyc = ms * 1e-3 * ghz * 1e9;                 // elapsed cycles
+  const double cyc = (double)cycles;                        // SM cycles of the slowest warp
   const double per_smsp = wide * warps_per_sm / 4.0;        // warp-instructions per sub-partition
   printf("{\"warps_per_sm\": %d, \"chains\": %d, \"len\": %d, \"ms\": %.3f, \"cycles_per_wide_per_warp\": %.2f, "
          "\"pipe_frac\": %.3f}\n", warps_per_sm, C, LEN, ms, cyc / wide, per_smsp * 4.0 / cyc);
@@ -73,11 +80,10 @@ void run(int warps_per_sm, uint32_t* d, int sms, double ghz) {
 int main() {
   cudaDeviceProp pr;
   cudaGetDeviceProperties(&pr, 0);
-  int khz = 0;
-  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
-  const double ghz = khz * 1e-6;
   uint32_t* d;
   cudaMalloc(&d, 64 << 20);
+  unsigned long long* ghz;  // device counter: max cycles over warps
+  cudaMalloc(&ghz, 8);
   for (int w : {4, 8, 12, 16}) {
     run<1, 16>(w, d, pr.multiProcessorCount, ghz);
     run<2, 16>(w, d, pr.multiProcessorCount, ghz);
