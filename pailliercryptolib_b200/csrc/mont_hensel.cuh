@@ -395,8 +395,10 @@ struct HMont {
           const uint4 bv = *reinterpret_cast<const uint4*>(b1s + i + k);
           uint4 cv = make_uint4(0, 0, 0, 0);
           if (TWO) cv = *reinterpret_cast<const uint4*>(b0s + i + k);
-          uint4 mv = *reinterpret_cast<const uint4*>(qs + i + k);
-          if (!l0) mv = make_uint4(0, 0, 0, 0);
+          // only the group's lane 0 injects the quotient digits (it also wrote them:
+          // program order, no other lane ever touches qs)
+          uint4 mv = make_uint4(0, 0, 0, 0);
+          if (l0) mv = *reinterpret_cast<const uint4*>(qs + i + k);
           in_limb = row64<MD>(Ew, Et, Ow, Ot, a, a2, n, bv.x, cv.x, mv.x, in_limb, n0inv, qd);
           in_limb = row64<MD>(Ow, Ot, Ew, Et, a, a2, n, bv.y, cv.y, mv.y, in_limb, n0inv, qd);
           in_limb = row64<MD>(Ew, Et, Ow, Ot, a, a2, n, bv.z, cv.z, mv.z, in_limb, n0inv, qd);
@@ -418,8 +420,10 @@ struct HMont {
           const uint4 bv = *reinterpret_cast<const uint4*>(b1s + i + k);
           uint4 cv = make_uint4(0, 0, 0, 0);
           if (TWO) cv = *reinterpret_cast<const uint4*>(b0s + i + k);
-          uint4 mv = *reinterpret_cast<const uint4*>(qs + i + k);
-          if (!l0) mv = make_uint4(0, 0, 0, 0);
+          // only the group's lane 0 injects the quotient digits (it also wrote them:
+          // program order, no other lane ever touches qs)
+          uint4 mv = make_uint4(0, 0, 0, 0);
+          if (l0) mv = *reinterpret_cast<const uint4*>(qs + i + k);
           in_limb = row<MD>(E, O, a, a2, n, bv.x, cv.x, mv.x, in_limb, n0inv, qd);
           in_limb = row<MD>(O, E, a, a2, n, bv.y, cv.y, mv.y, in_limb, n0inv, qd);
           in_limb = row<MD>(E, O, a, a2, n, bv.z, cv.z, mv.z, in_limb, n0inv, qd);

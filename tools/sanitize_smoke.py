@@ -57,5 +57,35 @@ for bits in ("1024", "2048"):
     assert np.array_equal(sk.decrypt(ct), pt)
     del os.environ["IPCLB200_DECRYPT"]
     assert np.array_equal(sk.decrypt(pk0.encrypt(pt, None, make_secure=False)), pt)
+
+# ---- round-2 kernels: every lane layout of the two-digit CRT decrypt (incl. the
+# thread-per-task kernel with its TMA fetch into the compact staging area), the
+# constant schedule, the two-digit ct*pt ladder, device-drawn randoms
+k = K["2048"]
+p, q = sorted((k["p"], k["q"]))
+n = p * q
+pk = capi.PubKey(to_limbs(n, 64), to_limbs(k["hs"], 128), 1024)
+sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+pt = random_limbs(rng, 37, 64, top_mask=0x3FFFFFFF)
+ct = pk.encrypt(pt, random_limbs(rng, 37, 2))
+for layout in ("-2", "-1", "0", "1", "2"):
+    os.environ["IPCLB200_HENSEL_SPREAD"] = layout
+    os.environ["IPCLB200_HENSEL_W64"] = "1"
+    assert np.array_equal(sk.decrypt(ct), pt), layout
+sk.set_schedule(True)
+os.environ["IPCLB200_HENSEL_SPREAD"] = "-2"
+assert np.array_equal(sk.decrypt(ct[:5]), pt[:5])
+del os.environ["IPCLB200_HENSEL_SPREAD"], os.environ["IPCLB200_HENSEL_W64"]
+nsq = to_limbs(n * n, 128)
+e = random_limbs(rng, 7, 2)
+got = batch_from_limbs(capi.modexp(ct[:7], e, nsq, capi.SHARED_MOD))
+assert got == [pow(c, x, n * n) for c, x in zip(batch_from_limbs(ct[:7]), batch_from_limbs(e))]
+key = rng.integers(0, 2**32, 8, dtype=np.uint64).astype(np.uint32)
+nonce = rng.integers(0, 2**32, 3, dtype=np.uint64).astype(np.uint32)
+c2 = pk.encrypt_drbg(pt[:9], key, nonce)
+assert np.array_equal(sk.decrypt(c2), pt[:9])
+b = capi.Batch(33, 18)
+b.random(561, key, nonce)
+assert b.download().shape == (33, 18)
 capi.shutdown()
 print("sanitize_smoke ok")
