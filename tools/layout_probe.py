@@ -1,6 +1,10 @@
-"""Timing probe: thread-per-task (T = 1) layout of the two-digit CRT decrypt
-against the shipped 16 x 2 layout.  Device-resident, CUDA events on the
-launching stream; one JSON line per configuration.  Run under gpurun."""
+"""Timing probe of the lane layouts of the two-digit CRT decrypt on one GPU:
+device-resident, CUDA events on the launching stream, one JSON line per (batch
+size, layout).  `python tools/layout_probe.py <key bits> <count> [<count> ...]`,
+layouts from PROBE_LAYOUTS (default "0,1,-2": 16 limbs x 2 lanes, 8 x 4, one task
+per thread).  profiles/r02_layout_sweep.jsonl and r02_layout_other_keys.jsonl are
+its output; the cost model pick_hensel_spread (csrc/host_common.hpp) is fitted to
+them.  Run under gpurun."""
 import json
 import os
 import sys
