@@ -239,7 +239,7 @@ inline void hensel_side_block(const Limbs& p, const Limbs& psq, const Limbs& hp,
 //     t = first[3] + (full - 1) * round + inc[w]     (otherwise)
 // Only the ratios between layouts matter, so the 2048-bit numbers serve every
 // key size.  Layout 2 keeps the simpler max(L, F * fill) model it was fitted
-// with (profiles/r02_hensel_small_batches.md).
+// with (profiles/r02_layout_small_batches.jsonl).
 struct HenselStair {
   double first[3], round, inc[3];
 };
