@@ -142,15 +142,19 @@ class PaillierPublicKey:
         r_words = 0
         if apply_obfuscator:
             if self.enable_DJN:
+                # the DJN randoms never exist on the host: one fresh 256-bit key and
+                # 96-bit nonce from the OS, expanded in HBM by the ChaCha20 generator
+                # (ipclb200_random_dev; getRandomBN per element in the reference,
+                # ipcl/pub_key.cpp:59-61)
                 r_words = (self.randbits + 31) // 32
-                rnd = np.frombuffer(secrets.token_bytes(4 * r_words * len(vals)),
-                                    dtype=np.uint32).reshape(len(vals), r_words).copy()
-                if self.randbits % 32:
-                    rnd[:, -1] &= np.uint32((1 << (self.randbits % 32)) - 1)
+                seed = np.frombuffer(secrets.token_bytes(44), dtype=np.uint32)
+                r = _DevBatch(len(vals), r_words)
+                capi.random_dev(r.ptr, len(vals), r_words, self.randbits, seed[:8], seed[8:],
+                                0, _stream())
             else:
                 r_words = self.nl
                 rnd = batch_to_limbs([1 + secrets.randbelow(self.n - 1) for _ in vals], self.nl)
-            r = _DevBatch.from_numpy(rnd)
+                r = _DevBatch.from_numpy(rnd)
         self._key.encrypt_dev(pt.ptr, self.nl, r.ptr if r else 0, r_words, len(vals),
                               ct.ptr, _stream(), make_secure=apply_obfuscator)
         return PaillierEncryptedNumber(self, ct)
