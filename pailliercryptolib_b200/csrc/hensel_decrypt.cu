@@ -14,11 +14,6 @@ template <int K, int T, int MINB, int ROWS, bool W64, int BT, bool COMPACT>
 void launch_one(const DecryptHenselParams& p, int grid, size_t smem, cudaStream_t s) {
   decrypt_hensel_kernel<K, T, MINB, ROWS, W64, BT, COMPACT><<<grid, BT, smem, s>>>(p);
 }
-template <int K, int T, int MAXR, int ROWS, bool W64, int BT>
-void launch_one_r(const DecryptHenselParams& p, int grid, size_t smem, cudaStream_t s) {
-  decrypt_hensel_kernel_r<K, T, MAXR, ROWS, W64, BT><<<grid, BT, smem, s>>>(p);
-}
-
 // grid = the blocks that are resident at once (persistent kernel, work is
 // claimed chunk by chunk), at most max_blocks per SM
 template <typename Kern>
@@ -63,15 +58,6 @@ cudaError_t plan_one(size_t count, int sms, int want_blocks, const char* name,
                      hensel_smem_bytes<K, T, COMPACT>(BT), T, BT,
                      want_blocks < MINB ? want_blocks : MINB, count, sms, out);
 }
-// register-capped variant: BLOCKS blocks of BT threads per SM
-template <int K, int T, int MAXR, int ROWS, bool W64, int BT, int BLOCKS>
-cudaError_t plan_one_r(size_t count, int sms, const char* name, HenselDecryptPlan* out) {
-  out->launch = launch_one_r<K, T, MAXR, ROWS, W64, BT>;
-  out->name = name;
-  return plan_kernel(decrypt_hensel_kernel_r<K, T, MAXR, ROWS, W64, BT>,
-                     hensel_smem_bytes<K, T>(BT), T, BT, BLOCKS, count, sms, out);
-}
-
 }  // namespace
 
 #define PLAN(K_, T_, MINB_, ROWS_, W64_)                                              \
@@ -83,10 +69,6 @@ cudaError_t plan_one_r(size_t count, int sms, const char* name, HenselDecryptPla
   return plan_one<K_, T_, MINB_, ROWS_, W64_, true>(                                     \
       count, sms, want_blocks,                                                           \
       "decrypt_hensel_kernel<" #K_ "," #T_ "," #MINB_ "," #ROWS_ "," #W64_ ",compact>", out)
-#define PLANR(K_, T_, MAXR_, ROWS_, W64_, BT_, BLOCKS_)                                  \
-  return plan_one_r<K_, T_, MAXR_, ROWS_, W64_, BT_, BLOCKS_>(                           \
-      count, sms, "decrypt_hensel_kernel_r<" #K_ "," #T_ "," #MAXR_ "," #ROWS_ "," #W64_ \
-                  "," #BT_ ">", out)
 
 cudaError_t hensel_decrypt_plan(int pl, int layout, int rows, bool w64, size_t count, int sms,
                                 int want_blocks, HenselDecryptPlan* out) {
@@ -98,9 +80,7 @@ cudaError_t hensel_decrypt_plan(int pl, int layout, int rows, bool w64, size_t c
       if (layout >= 2) PLAN(4, 8, 3, 8, false);
       if (layout == 1) PLAN(8, 4, 3, 8, false);
       if (layout == -2) PLANC(32, 1, 3, 4, true);
-      if (layout == -3) PLANC(32, 1, 2, 4, true);
-      if (layout == -1 && w64) PLAN(32, 1, 2, 4, true);
-      if (layout == -1) PLAN(32, 1, 2, 4, false);
+      if (layout == -1) PLAN(32, 1, 2, 4, true);  // with the prefetch buffer: 8 warps per SM
       if (rows == 4) PLAN(16, 2, 3, 4, false);
       if (w64) PLAN(16, 2, 3, 8, true);
       PLAN(16, 2, 3, 8, false);
@@ -115,7 +95,6 @@ cudaError_t hensel_decrypt_plan(int pl, int layout, int rows, bool w64, size_t c
   }
 }
 #undef PLAN
-#undef PLANR
 #undef PLANC
 
 }  // namespace ipclb200

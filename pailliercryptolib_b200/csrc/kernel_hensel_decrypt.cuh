@@ -54,14 +54,6 @@ __global__ void __launch_bounds__(BT, MINB)
   decrypt_hensel_body<K, T, ROWS, W64, COMPACT>(p);
 }
 
-// the same kernel under a register cap instead of a blocks-per-SM hint (ptxas
-// turns __launch_bounds__(64, 5) into 168 registers and spills; 200 fit)
-template <int K, int T, int MAXR, int ROWS, bool W64, int BT>
-__global__ void __launch_bounds__(BT) __maxnreg__(MAXR)
-    decrypt_hensel_kernel_r(const DecryptHenselParams p) {
-  decrypt_hensel_body<K, T, ROWS, W64, false>(p);
-}
-
 template <int K, int T, int ROWS, bool W64, bool COMPACT>
 __device__ __forceinline__ void decrypt_hensel_body(const DecryptHenselParams& p) {
   using M = Mont<K, T>;
