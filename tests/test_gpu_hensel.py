@@ -118,6 +118,27 @@ def test_hensel_layouts_agree_with_pow(capi, all_keys, name, layout, monkeypatch
     assert batch_from_limbs(sk.decrypt(ct)) == got
 
 
+@pytest.mark.parametrize("count", [14337, 24577, 45057])
+def test_ragged_large_batches_take_the_thread_per_task_layout(capi, all_keys, count):
+    """batch sizes just past a boundary of the layout cost model that are not a
+    multiple of the 32 tasks of a warp: the automatic choice is the
+    thread-per-task kernel, the last warp of each side is partly idle; every
+    plaintext must come back, a sample is checked against Python pow()"""
+    assert capi.decrypt_layout(count, 32, 148) == -2
+    k = all_keys["2048"]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    rng = np.random.default_rng(count)
+    pk = capi.PubKey(to_limbs(n, 64), to_limbs(k["hs"], 128), 1024)
+    sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
+    pt = random_limbs(rng, count, 64, top_mask=0x3FFFFFFF)
+    ct = pk.encrypt(pt, random_limbs(rng, count, 32))
+    got = sk.decrypt(ct)
+    assert np.array_equal(got, pt)
+    cts = batch_from_limbs(ct[-3:])
+    assert batch_from_limbs(got[-3:]) == [dec_crt(p, q, c) for c in cts]
+
+
 def test_full_batch_65536_bit_exact_vs_oracle(capi, oracle, keys):
     """BASELINE.json configs[1] at full size, every element compared bit for bit
     with the oracle (AVX512-IFMA mb8 restatement, itself pinned to the ISO KAT
