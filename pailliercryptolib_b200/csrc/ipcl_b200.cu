@@ -1221,6 +1221,33 @@ int encrypt_dev_impl(Op& op, const ipclb200_pubkey* pk, const uint32_t* d_pt, in
       p.mode = 2;
       p.window = pick_window(r_bits);
     }
+  } else if (modexp_hensel_applies(*pd->msq, count, hbn::bitlen(pk->n)) && d_r &&
+             r_words <= L) {
+    // non-DJN: obf = r^n mod n^2 (ipcl/pub_key.cpp:66-80) by the two-digit ladder
+    // (K1h: half the multiplies of the full-width kernel), ct = (n*m + 1) * obf.
+    // r zero-extended to the 2*nl words of a residue mod n^2; n as the one exponent.
+    uint32_t *d_base = nullptr, *d_obf = nullptr;
+    TRY(op.words(count * (size_t)L, &d_base));
+    TRY(op.words(count * (size_t)L, &d_obf));
+    if (r_words < L) {
+      CUDA_TRY(cudaMemsetAsync(d_base, 0, count * (size_t)L * 4, op.s));
+      CUDA_TRY(cudaMemcpy2DAsync(d_base, (size_t)L * 4, d_r, (size_t)r_words * 4,
+                                 (size_t)r_words * 4, count, cudaMemcpyDeviceToDevice, op.s));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(d_base, d_r, count * (size_t)L * 4, cudaMemcpyDeviceToDevice,
+                               op.s));
+    }
+    TRY(launch_modexp_hensel(op, *pd->msq, d_base, p.n_exp, 0, pk->nl, hbn::bitlen(pk->n), count,
+                             d_obf));
+    TRY(encrypt_dev_impl(op, pk, d_pt, pt_words, nullptr, 0, 0, count, 0, d_ct));  // n*m + 1
+    ModmulParams mm{};
+    mm.a = d_ct;
+    mm.b = d_obf;
+    mm.b_stride = L;
+    mm.m = pd->msq->mc;
+    mm.out = d_ct;
+    mm.count = count;
+    return launch_modmul(op, mm, L);
   } else {
     p.mode = 3;
     const char* ns = getenv("IPCLB200_NO_SCHED");
@@ -1468,7 +1495,14 @@ int decrypt_dev_impl(Op& op, const ipclb200_privkey* sk, const uint32_t* d_ct, s
     p.out = d_x;
     p.count = count;
     if (!secret_schedule_is_constant(sk)) p.sched = pp.sched_lambda;
-    TRY(launch_modexp(op, p, L));
+    if (modexp_hensel_applies(*sd->mnsq, count, sk->lambda_bits) && L == 4 * pl) {
+      // ct^lambda mod n^2 by the two-digit ladder (fixed windows: the operation
+      // sequence depends on the bit length of lambda only)
+      TRY(launch_modexp_hensel(op, *sd->mnsq, d_ct, pp.lambda, 0, 2 * pl, sk->lambda_bits, count,
+                               d_x));
+    } else {
+      TRY(launch_modexp(op, p, L));
+    }
     RawFinishParams f{};
     f.x = d_x;
     f.n = pp.n;

@@ -254,6 +254,36 @@ def test_encrypt_decrypt_batch_vs_oracle(capi, oracle, keys, bits, layout):
     assert np.array_equal(c_w, oracle.encrypt(nl, hsl, pt[:70], r_wide))
 
 
+@pytest.mark.parametrize("bits,count", [("1024", 2500), ("2048", 2051)])
+def test_non_djn_encrypt_two_digit_ladder_vs_oracle(capi, oracle, keys, bits, count, monkeypatch):
+    """non-DJN keys (the reference's default PublicKey): obf = r^n mod n^2
+    (ipcl/pub_key.cpp:66-80).  From 2048 elements on the library computes it with
+    the two-digit ladder + n*m+1 + one modmul instead of the full-width fused
+    kernel: same ciphertexts from both, equal to the oracle, decryptable"""
+    k = keys[bits]
+    p, q = sorted((k["p"], k["q"]))
+    n = p * q
+    NL = int(bits) // 32
+    rng = np.random.default_rng(int(bits) + count)
+    pt = random_limbs(rng, count, NL, top_mask=0x3FFFFFFF)
+    r = batch_to_limbs([1 + int.from_bytes(rng.bytes(NL * 4), "little") % (n - 1)
+                        for _ in range(count)], NL)
+    nl = to_limbs(n, NL)
+    pk = capi.PubKey(nl)
+    ct = pk.encrypt(pt, r)
+    monkeypatch.setenv("IPCLB200_NO_HENSEL_MODEXP", "1")
+    assert np.array_equal(pk.encrypt(pt, r), ct)  # the full-width fused kernel
+    monkeypatch.delenv("IPCLB200_NO_HENSEL_MODEXP")
+    assert np.array_equal(ct[:300], oracle.encrypt(nl, None, pt[:300], r[:300]))
+    assert np.array_equal(ct[-5:], oracle.encrypt(nl, None, pt[-5:], r[-5:]))
+    sk = capi.PrivKey(to_limbs(p, NL // 2), to_limbs(q, NL // 2))
+    assert np.array_equal(sk.decrypt(ct), pt)
+    # RAW decrypt (ipcl/pri_key.cpp:92-111) takes the same ladder for ct^lambda
+    assert np.array_equal(sk.decrypt(ct, use_crt=False), pt)
+    monkeypatch.setenv("IPCLB200_NO_HENSEL_MODEXP", "1")
+    assert np.array_equal(sk.decrypt(ct[:2048], use_crt=False), pt[:2048])
+
+
 def test_comb_table_upgrade_keeps_results(capi, oracle, keys, monkeypatch):
     """a DJN key starts with the small fixed-base table (8-bit windows) and moves
     to the wide one after IPCLB200_COMB_UPGRADE elements: same ciphertexts from
