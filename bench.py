@@ -13,6 +13,8 @@ own benchmark uses (benchmark/bench_cryptography.cpp:24-36).
   e2e   : the same step through the host-pointer C ABI (ipclb200_encrypt +
           ipclb200_decrypt) from pinned host buffers, copies inside the timing,
           over all `steps`
+  e2e_ipcl : the same step through the C++ ipcl:: API an unmodified IPCL
+          application calls (host BigNumbers in, host BigNumbers out; N = 1 only)
   roofline : the dominant kernel (two-digit CRT decrypt) against the measured
           IMAD.WIDE rate of this GPU (the path is integer-ALU bound, SURVEY.md
           section 8d): algorithmic fraction (generic w=5 modexp count) and the
@@ -32,6 +34,7 @@ own benchmark uses (benchmark/bench_cryptography.cpp:24-36).
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -277,6 +280,35 @@ def run_reference(args):
     emit_json(line)
 
 
+def ipcl_e2e(batch, steps):
+    """The headline workload through the C++ ipcl:: API (vector<BigNumber> in,
+    vector<BigNumber> out, benchmarks/bench_ipcl.cpp --e2e) in a child process:
+    once with device-resident texts (the library's default: the ciphertexts stay
+    in HBM between encrypt and decrypt) and once with a host round trip of every
+    text (IPCL_B200_DEVICE_RESIDENT=0)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "bench_ipcl")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/cpp/_build/bench_ipcl not built"}
+    out = {"unit": UNIT, "batch": batch, "steps": steps,
+           "api": "ipcl::PublicKey::encrypt -> ipcl::PrivateKey::decrypt -> getTexts(), "
+                  "wall clock in the C++ caller, PlainText built from host BigNumbers every "
+                  "step, all plaintexts compared with their inputs"}
+    for key, resident in (("resident_texts", "1"), ("host_round_trip", "0")):
+        env = dict(os.environ, IPCL_B200_DEVICE_RESIDENT=resident, IPCLB200_COMB_SYNC="1")
+        env.pop("OMP_NUM_THREADS", None)
+        try:
+            r = subprocess.run([exe, "--e2e", str(batch), str(steps)], env=env, text=True,
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[key] = {"value": d["pairs_per_s"], "ms_per_step": d["ms_per_step"],
+                        "mismatches": d["mismatches"]}
+        except Exception as e:  # reported, never fatal for the headline
+            out[key] = {"error": repr(e)[:200]}
+    if "value" in out.get("resident_texts", {}):
+        out["value"] = out["resident_texts"]["value"]
+    return out
+
+
 def emit_json(line):
     """stdout carries exactly ONE line: the JSON.  Libraries that write to the
     C-level stdout (NCCL prints its version banner there) were redirected to
@@ -441,11 +473,11 @@ def run_configs(torch, capi, peak_mac, quick):
                 "oracle_check": {"elements": S, "ok": ok}})
     for ebits, label in ((32, "32-bit plaintexts"), (2048, "2048-bit plaintexts")):
         ew = max(1, ebits // 32)
-        cnt = count if ebits == 32 else (4096 if quick else 16384)
+        cnt = count if ebits == 32 else (4096 if quick else BATCH)
         e = random_limbs(rng, cnt, ew)
         d_e = cuda(e)
         ms = timed(lambda: capi.modexp_dev(d_a.data_ptr(), d_e.data_ptr(), nsq, ew, ebits, cnt,
-                                           d_o.data_ptr(), stream), 2)
+                                           d_o.data_ptr(), stream), 2 if ebits == 32 else 1)
         S2 = 1024
         want = (orc.modexp_mb8(host(d_a[:S2]), e[:S2], nsq) if fast else
                 orc.modexp(host(d_a[:S2]), e[:S2], nsq[None, :], shared_mod=True))
@@ -524,6 +556,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-ipcl", action="store_true", help="skip the e2e_ipcl leg")
     ap.add_argument("--quick", action="store_true", help="smaller side measurements")
     args = ap.parse_args()
 
@@ -676,6 +709,9 @@ def main():
                         "host-pointer C ABI (copies inside the timing)" % got,
             "devices": got, "ms_per_step": ms, "value": BATCH / (ms * 1e-3), "unit": UNIT}
         capi.init_devices(1) if local == 0 else None
+    e2e_ipcl = None
+    if rank == 0 and world == 1 and not args.no_ipcl:
+        e2e_ipcl = ipcl_e2e(BATCH, max(1, min(args.steps, 5)))
     configs = None
     if rank == 0 and not args.no_configs:
         torch.cuda.set_device(local)
@@ -774,6 +810,8 @@ def main():
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
+        if e2e_ipcl is not None:
+            line["e2e_ipcl"] = e2e_ipcl
         if strong is not None:
             line["strong"] = strong
         if configs is not None:

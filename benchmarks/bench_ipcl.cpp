@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <thread>
@@ -60,8 +61,45 @@ void report(const char* name, size_t n, double us) {
 
 }  // namespace
 
+// --e2e N STEPS: the headline workload (BASELINE configs[1]) exactly as an
+// unmodified IPCL application runs it: N host BigNumbers -> PublicKey::encrypt ->
+// PrivateKey::decrypt -> N host BigNumbers, every plaintext compared with its
+// input afterwards.  One JSON line; bench.py reports it as "e2e_ipcl".
+int run_e2e(size_t dsize, int steps) {
+  const BigNumber n = P_BN * Q_BN;
+  ipcl::PublicKey pk(n, n.BitSize(), true);
+  ipcl::PrivateKey sk(pk, P_BN, Q_BN);
+  pk.setHS(HS_BN);
+  std::vector<BigNumber> v(dsize);
+  for (size_t i = 0; i < dsize; i++) v[i] = P_BN - BigNumber((unsigned int)(i * 1024));
+  std::vector<BigNumber> got;
+  auto one = [&] {
+    ipcl::PlainText pt(v);  // fresh text per step: its upload is inside the timing
+    ipcl::CipherText ct = pk.encrypt(pt);
+    ipcl::PlainText dt = sk.decrypt(ct);
+    got = dt.getTexts();  // all N results as host BigNumbers
+  };
+  for (int w = 0; w < 3; w++) one();  // warm-up: device key, fixed-base table tiers
+  auto a = std::chrono::steady_clock::now();
+  for (int s = 0; s < steps; s++) one();
+  auto b = std::chrono::steady_clock::now();
+  const double ms = std::chrono::duration<double>(b - a).count() * 1e3 / steps;
+  size_t bad = got.size() == dsize ? 0 : dsize;
+  for (size_t i = 0; i < dsize && !bad; i++) bad += got[i] != v[i];
+  const char* res = std::getenv("IPCL_B200_DEVICE_RESIDENT");
+  std::printf("{\"benchmark\": \"E2E_encrypt_decrypt\", \"batch\": %zu, \"steps\": %d, "
+              "\"ms_per_step\": %.3f, \"pairs_per_s\": %.1f, \"mismatches\": %zu, "
+              "\"device_resident_texts\": %s}\n",
+              dsize, steps, ms, dsize / ms * 1e3, bad,
+              (res && res[0] == '0') ? "false" : "true");
+  ipcl::terminateContext();
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   ipcl::initializeContext("default");
+  if (argc > 1 && std::string(argv[1]) == "--e2e")
+    return run_e2e(argc > 2 ? std::stoul(argv[2]) : 65536, argc > 3 ? std::stoi(argv[3]) : 5);
   std::vector<size_t> sizes = {16, 64, 128, 256, 512, 1024, 2048, 2100, 65536};
   if (argc > 1) {
     sizes.clear();

@@ -133,9 +133,6 @@ bool deviceResidentEnabled() {
 
 }  // namespace detail
 
-// lazy host materialisation happens inside const accessors that several
-// threads may call on one text; one process-wide lock is enough (it is taken
-// once per text)
 // Lazy host materialisation happens inside const accessors that several
 // threads may call on one text.  The lock is held while a download completes,
 // so it must not be shared between unrelated texts (four callers working on
