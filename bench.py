@@ -11,8 +11,10 @@ own benchmark uses (benchmark/bench_cryptography.cpp:24-36).
           launching stream); under torchrun every rank has its own 65536-element
           shard (weak scaling), value = all units / max-over-ranks time
   e2e   : the same step through the host-pointer C ABI (ipclb200_encrypt +
-          ipclb200_decrypt) from pinned host buffers, copies inside the timing,
-          over all `steps`
+          ipclb200_decrypt) from pinned host buffers, transfers inside the
+          timing, over all `steps` (the library uses pinned operands in place:
+          the kernels move them over PCIe while they compute; the same steps
+          with staging copies are reported as e2e.staged_copies)
   e2e_ipcl : the same step through the C++ ipcl:: API an unmodified IPCL
           application calls (host BigNumbers in, host BigNumbers out; N = 1 only)
   roofline : the dominant kernel (two-digit CRT decrypt) against the measured
@@ -663,19 +665,30 @@ def main():
     launches = capi.launch_count() - launches0
     step_ms = float(np.sum(enc_ms) + np.sum(dec_ms)) / args.steps
     # ---- timed: end to end through the host-pointer C ABI, all steps ---------
-    step_e2e()   # warm
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    # The pinned caller buffers are used in place by the kernels (zero-copy over
+    # PCIe, include/ipcl_b200.h: ipclb200_zero_copy_count); the same steps with
+    # staging copies before / after every launch are timed next to it.
+    def time_e2e():
+        step_e2e()   # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        return (time.perf_counter() - t0) * 1e3 / args.steps
+
+    os.environ["IPCLB200_ZERO_COPY"] = "0"
+    e2e_staged_ms = time_e2e()
+    del os.environ["IPCLB200_ZERO_COPY"]
+    zc0 = capi.zero_copy_count()
+    e2e_ms = time_e2e()
+    in_place = (capi.zero_copy_count() - zc0) / (args.steps + 1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert np.array_equal(dt_pin.numpy().view(np.uint32), pt_h), "e2e round trip failed"
 
-    step_ms, e2e_ms, enc_mean, dec_mean = sharding.max_over_ranks(
-        [step_ms, e2e_ms, float(np.mean(enc_ms)), float(np.mean(dec_ms))], dev)
+    step_ms, e2e_ms, enc_mean, dec_mean, e2e_staged_ms = sharding.max_over_ranks(
+        [step_ms, e2e_ms, float(np.mean(enc_ms)), float(np.mean(dec_ms)), e2e_staged_ms], dev)
     del d_ct, d_dt, flush
 
     # ---- strong scaling: one batch owned by rank 0 ---------------------------
@@ -804,7 +817,16 @@ def main():
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms, "steps": args.steps,
                     "h2d_bytes_per_step": B * (NL + RL + 2 * NL) * 4,
-                    "d2h_bytes_per_step": B * (2 * NL + NL) * 4},
+                    "d2h_bytes_per_step": B * (2 * NL + NL) * 4,
+                    "in_place_operands_per_step": in_place,
+                    "transfer": "encrypt reads its plaintexts and writes its ciphertexts "
+                                "through the mapped pinned buffers while it runs; randoms, "
+                                "the ciphertexts of decrypt and the decrypted plaintexts go "
+                                "by copy engines",
+                    "staged_copies": {"value": total / (e2e_staged_ms * 1e-3),
+                                      "ms_per_step": e2e_staged_ms,
+                                      "note": "IPCLB200_ZERO_COPY=0: every operand staged "
+                                              "by a copy before / after the launch"}},
             "gpu_launches": launches,
             "roofline": roofline,
             "clocks": sampler.summary(),

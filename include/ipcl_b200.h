@@ -302,6 +302,18 @@ int ipclb200_int_peak(double* mac32_per_s, double* sm_clock_mhz);
  * runs for hundreds of milliseconds (int_peak is the burst figure) */
 int ipclb200_int_peak_sustained(double seconds, double* mac32_per_s);
 uint64_t ipclb200_launch_count(void);
+/* Operands of host-pointer calls used IN PLACE so far.  ipclb200_encrypt (DJN
+ * keys) on batches of >= 1024 elements per device does not stage page-locked
+ * caller buffers (cudaHostAlloc / cudaHostRegister / ipclb200_host_alloc
+ * memory): the kernel reads the plaintexts and writes the ciphertexts through
+ * the mapped alias of the buffers, element by element as it claims work, so the
+ * PCIe transfer overlaps the arithmetic (the role of the QAT path's in-place
+ * request buffers, module/heqat/heqat/include/heqat/bnops.h:121-148).  Pageable
+ * buffers are staged by copies as before.  IPCLB200_ZERO_COPY is a bit mask:
+ * 1 = encrypt plaintexts, 2 = encrypt ciphertexts, 4 = ciphertexts of the CRT
+ * decrypt (measured slower than the staged copy, hence default 3); 0 stages
+ * everything. */
+uint64_t ipclb200_zero_copy_count(void);
 
 /* Pipe-overlap probe (profiles/r01_pipe_overlap.md): time of a fixed number of
  * IMAD.WIDE chains (mode 0), DFMA chains (1), both kinds on every SM

@@ -45,7 +45,7 @@ EXPORTS = [
     "ipclb200_modexp_batch", "ipclb200_host_alloc", "ipclb200_host_free",
     "ipclb200_batch_touch", "ipclb200_privkey_set_schedule",
     "ipclb200_random_dev", "ipclb200_batch_random", "ipclb200_encrypt_drbg",
-    "ipclb200_decrypt_layout",
+    "ipclb200_decrypt_layout", "ipclb200_zero_copy_count",
 ]
 
 
@@ -63,6 +63,7 @@ def lib():
         L.ipclb200_last_error.restype = ctypes.c_char_p
         L.ipclb200_version.restype = ctypes.c_char_p
         L.ipclb200_launch_count.restype = ctypes.c_uint64
+        L.ipclb200_zero_copy_count.restype = ctypes.c_uint64
         L.ipclb200_batch_count.restype = ctypes.c_size_t
         L.ipclb200_stream.restype = ctypes.c_void_p
         _lib = L
@@ -121,6 +122,10 @@ def launch_count():
     return int(lib().ipclb200_launch_count())
 
 
+def zero_copy_count():
+    return int(lib().ipclb200_zero_copy_count())
+
+
 def int_peak():
     macs, mhz = ctypes.c_double(), ctypes.c_double()
     _check(lib().ipclb200_int_peak(ctypes.byref(macs), ctypes.byref(mhz)))
@@ -146,6 +151,34 @@ def pipe_mix(mode):
     ms = ctypes.c_double()
     _check(lib().ipclb200_pipe_mix(int(mode), ctypes.byref(ms)))
     return ms.value
+
+
+class _PinnedOwner:
+    """keeps a page-locked allocation alive for the numpy array built on it"""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.ipclb200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint32):
+    """numpy array in page-locked host memory (ipclb200_host_alloc).  The
+    host-pointer entry points use such buffers in place (zero-copy over PCIe)
+    for large batches; pageable arrays are staged by copies."""
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = ctypes.c_void_p()
+    _check(lib().ipclb200_host_alloc(ctypes.c_size_t(max(nbytes, 16)), ctypes.byref(ptr)))
+    owner = _PinnedOwner(ptr)
+    buf = (ctypes.c_ubyte * max(nbytes, 16)).from_address(ptr.value)
+    buf._owner = owner   # the ctypes buffer is the numpy array's base object
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def modexp(base, exp, mod, flags=0):

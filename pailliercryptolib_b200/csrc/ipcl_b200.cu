@@ -89,6 +89,7 @@ struct Runtime {
   std::vector<int> active;  // device ordinals host-pointer batches are split over
   bool active_set = false;
   std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> zero_copies{0};
   std::atomic<uint64_t> use_clock{0};
   Runtime() {
     for (auto& d : dev) d.store(nullptr);
@@ -483,6 +484,45 @@ int download_padded(uint32_t* h, const uint32_t* d, int words, int L, size_t cou
                                count, cudaMemcpyDeviceToHost, s));
   }
   return 0;
+}
+
+// Zero-copy: the device-visible alias of a caller's PAGE-LOCKED host buffer
+// (cudaHostAlloc / cudaHostRegister memory is mapped under unified addressing),
+// or nullptr for pageable memory.  Large host-pointer batches whose operands a
+// kernel touches exactly once per element (plaintexts in, ciphertexts in / out)
+// are read and written over PCIe by the kernel itself, element by element as
+// they are claimed, instead of being staged by a copy before and after the
+// launch: the transfer hides behind the arithmetic.  Measured at 65536 elements
+// and a 2048-bit key (profiles/r02_zero_copy_probe.jsonl): encrypt 12.67 ->
+// 11.83 ms with plaintexts and ciphertexts in place; the CRT decrypt LOSES 0.7 ms
+// when it reads its ciphertexts in place (one task per thread: 16-byte pieces
+// 512 bytes apart, each ciphertext once per side), so that class is off unless
+// asked for.  IPCLB200_ZERO_COPY = bit mask of the classes below (default 3,
+// 0 = stage everything).  The device of the shard must be current.
+constexpr size_t kZeroCopyMin = 1024;
+// operand classes (bits of IPCLB200_ZERO_COPY, default all)
+constexpr int kZcEncryptIn = 1, kZcEncryptOut = 2, kZcDecryptIn = 4;
+bool zero_copy_enabled(int which) {
+  const char* e = getenv("IPCLB200_ZERO_COPY");
+  return ((e && *e ? atoi(e) : (kZcEncryptIn | kZcEncryptOut)) & which) != 0;
+}
+uint32_t* mapped_alias(const void* h, size_t bytes, int which) {
+  if (!zero_copy_enabled(which) || !h || bytes == 0) return nullptr;
+  cudaPointerAttributes a0{}, a1{};
+  if (cudaPointerGetAttributes(&a0, h) != cudaSuccess ||
+      cudaPointerGetAttributes(&a1, static_cast<const char*>(h) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer ||
+      !a1.devicePointer)
+    return nullptr;
+  // one contiguous mapping
+  if (static_cast<char*>(a1.devicePointer) - static_cast<char*>(a0.devicePointer) !=
+      (ptrdiff_t)(bytes - 1))
+    return nullptr;
+  g.zero_copies++;
+  return static_cast<uint32_t*>(a0.devicePointer);
 }
 
 // ---------------------------------------------------------------------------
@@ -1779,6 +1819,7 @@ void ipclb200_shutdown(void) {
 }
 
 uint64_t ipclb200_launch_count(void) { return g.launches.load(); }
+uint64_t ipclb200_zero_copy_count(void) { return g.zero_copies.load(); }
 
 // ---- modexp ---------------------------------------------------------------
 int ipclb200_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
@@ -1990,6 +2031,8 @@ int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt, int pt_words
   DeviceGuard guard;
   const int L = pk->L, CW = 2 * pk->nl;
   const int r_bits = make_secure ? max_bits(r, r_words, count, r_words) : 0;
+  const char* no_comb = getenv("IPCLB200_NO_COMB");
+  const bool zc = make_secure && pk->djn && L == CW && !(no_comb && no_comb[0] == '1');
   std::vector<Shard> shards;
   TRY(plan_shards(count, &shards));
   std::vector<Op> ops(shards.size());
@@ -1997,19 +2040,30 @@ int ipclb200_encrypt(const ipclb200_pubkey* pk, const uint32_t* pt, int pt_words
     const Shard& sh = shards[i];
     Op& op = ops[i];
     TRY(op.open(sh.dev));
-    uint32_t *d_pt, *d_r = nullptr, *d_ct;
-    TRY(op.words(sh.count * (size_t)pt_words, &d_pt));
-    TRY(op.words(sh.count * (size_t)L, &d_ct));
-    CUDA_TRY(cudaMemcpyAsync(d_pt, pt + sh.begin * (size_t)pt_words,
-                             sh.count * (size_t)pt_words * 4, cudaMemcpyHostToDevice, op.s));
+    uint32_t *d_pt = nullptr, *d_r = nullptr, *d_ct = nullptr;
+    const uint32_t* h_pt = pt + sh.begin * (size_t)pt_words;
+    uint32_t* h_ct = ct + sh.begin * (size_t)CW;
+    // The DJN fixed-base kernels read a plaintext and write a ciphertext once per
+    // element: page-locked caller buffers are used in place (mapped_alias above).
+    // The randoms are read window by window and always staged.
+    const bool in_place = zc && sh.count >= kZeroCopyMin;
+    if (in_place) d_pt = mapped_alias(h_pt, sh.count * (size_t)pt_words * 4, kZcEncryptIn);
+    if (!d_pt) {
+      TRY(op.words(sh.count * (size_t)pt_words, &d_pt));
+      CUDA_TRY(cudaMemcpyAsync(d_pt, h_pt, sh.count * (size_t)pt_words * 4,
+                               cudaMemcpyHostToDevice, op.s));
+    }
     if (make_secure) {
       TRY(op.words(sh.count * (size_t)r_words, &d_r));
       CUDA_TRY(cudaMemcpyAsync(d_r, r + sh.begin * (size_t)r_words,
                                sh.count * (size_t)r_words * 4, cudaMemcpyHostToDevice, op.s));
     }
+    if (in_place) d_ct = mapped_alias(h_ct, sh.count * (size_t)CW * 4, kZcEncryptOut);
+    const bool ct_in_place = d_ct != nullptr;
+    if (!ct_in_place) TRY(op.words(sh.count * (size_t)L, &d_ct));
     TRY(encrypt_dev_impl(op, pk, d_pt, pt_words, d_r, r_words, r_bits, sh.count, make_secure,
                          d_ct));
-    TRY(download_padded(ct + sh.begin * (size_t)CW, d_ct, CW, L, sh.count, op.s));
+    if (!ct_in_place) TRY(download_padded(h_ct, d_ct, CW, L, sh.count, op.s));
   }
   for (auto& op : ops) TRY(op.sync());
   return 0;
@@ -2261,6 +2315,8 @@ int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct, size_t coun
   // the kernels read a ciphertext as 2L (CRT, L = class of p^2) or Lnsq (RAW)
   // words; zero padding keeps the value
   const int ctw = use_crt ? 2 * sk->L : sk->Lnsq;
+  const bool zc = use_crt && sk->hensel_ok && sk->L == 2 * pl && CW == ctw &&
+                  !getenv("IPCLB200_DECRYPT");
   std::vector<Shard> shards;
   TRY(plan_shards(count, &shards));
   std::vector<Op> ops(shards.size());
@@ -2268,10 +2324,18 @@ int ipclb200_decrypt(const ipclb200_privkey* sk, const uint32_t* ct, size_t coun
     const Shard& sh = shards[i];
     Op& op = ops[i];
     TRY(op.open(sh.dev));
-    uint32_t *d_ct, *d_pt;
-    TRY(op.words(sh.count * (size_t)ctw, &d_ct));
+    uint32_t *d_ct = nullptr, *d_pt;
+    const uint32_t* h_ct = ct + sh.begin * (size_t)CW;
+    // the two-digit CRT kernel reads a ciphertext once per side, in its prologue:
+    // a page-locked caller buffer can be read in place (mapped_alias above; off by
+    // default, the staged copy is faster)
+    if (zc && sh.count >= kZeroCopyMin)
+      d_ct = mapped_alias(h_ct, sh.count * (size_t)CW * 4, kZcDecryptIn);
+    if (!d_ct) {
+      TRY(op.words(sh.count * (size_t)ctw, &d_ct));
+      TRY(upload_padded(d_ct, h_ct, CW, ctw, sh.count, op.s));
+    }
     TRY(op.words(sh.count * (size_t)(2 * pl), &d_pt));
-    TRY(upload_padded(d_ct, ct + sh.begin * (size_t)CW, CW, ctw, sh.count, op.s));
     TRY(decrypt_dev_impl(op, sk, d_ct, sh.count, use_crt, d_pt));
     CUDA_TRY(cudaMemcpyAsync(pt + sh.begin * (size_t)(2 * pl), d_pt,
                              sh.count * (size_t)(2 * pl) * 4, cudaMemcpyDeviceToHost, op.s));
