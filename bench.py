@@ -128,15 +128,30 @@ def sliding_counts(e, w=5):
     return nsq, nmul
 
 
+def hensel_window(p, q):
+    """the sliding-window width ipclb200_privkey_create picks for the two-digit
+    decrypt: fewest half-width products over both sides, 4..6 bits"""
+    def cost(w):
+        c = 0
+        for pr in (p, q):
+            nsq, nmul = sliding_counts(pr - 1, w)
+            c += 4 * nsq + 5 * (nmul + (1 << (w - 1)) - 1)
+        return c
+    return min((4, 5, 6), key=cost)
+
+
 def hensel_executed_macs(p, q):
     """IMAD.WIDE the two-digit decrypt executes per ciphertext (mont_hensel.cuh):
-    a squaring is 4 LH^2 + LH, a multiply 5 LH^2, per side one squaring + 15
-    multiplies for the table, 16 LH^2 to enter and 2 LH^2 to leave"""
+    a squaring is 4 LH^2 + LH, a multiply 5 LH^2, per side one squaring and
+    2^(w-1) - 1 multiplies for the table of odd powers, 16 LH^2 to enter and
+    2 LH^2 to leave"""
     total = 0
+    w = hensel_window(p, q)
     for pr in (p, q):
         LH = (pr.bit_length() + 31) // 32
-        nsq, nmul = sliding_counts(pr - 1)
-        total += (nsq + 1) * (4 * LH * LH + LH) + (nmul + 15) * 5 * LH * LH + 18 * LH * LH
+        nsq, nmul = sliding_counts(pr - 1, w)
+        total += ((nsq + 1) * (4 * LH * LH + LH) + (nmul + (1 << (w - 1)) - 1) * 5 * LH * LH +
+                  18 * LH * LH)
     return total
 
 

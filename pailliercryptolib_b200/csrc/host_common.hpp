@@ -129,6 +129,9 @@ inline int pick_window(int ebits) {
 }
 
 constexpr int kSchedWindow = 5;  // 16 odd powers per table
+// decrypt_hensel_kernel takes its table size from the schedule: window chosen per
+// key in this range (ipclb200_privkey_create)
+constexpr int kHenselMinWindow = 4, kHenselMaxWindow = 6;
 
 // left-to-right sliding-window schedule for a fixed exponent (format: see
 // modexp_sched_core in kernels.cuh).  e > 0.

@@ -729,6 +729,7 @@ struct ipclb200_privkey {
   size_t off_sched_q = 0, off_prog_p = 0, off_prog_q = 0, off_sched_lambda = 0;
   std::vector<uint32_t> h_hensel;  // 10*pl per side, then the run schedules
   size_t off_hsched_p = 0, off_hsched_q = 0;        // sliding window
+  int hensel_entries = 16;                          // odd powers per task table
   size_t off_hfixed_p = 0, off_hfixed_q = 0;        // constant schedule
   std::atomic<int> constant_schedule{0};            // ipclb200_privkey_set_schedule
   bool hensel_ok = false;
@@ -1377,7 +1378,7 @@ int decrypt_hensel_impl(Op& op, const ipclb200_privkey* sk, const PrivDev* sd,
   p.s1.n0inv = sk->q_n0inv;
   p.mpq = d_mpq;
   p.count = count;
-  p.table_entries = 1 << (kSchedWindow - 1);
+  p.table_entries = sk->hensel_entries;
   // blocks of 128 threads per SM: 3 (12 warps) saturate the multiplier pipe
   // (measured: 1/2/3 blocks -> 139.6/97.0/92.4 ms per 65536 at a 2048-bit key)
   int want_blocks = 3;
@@ -2266,7 +2267,34 @@ int ipclb200_privkey_create(const uint32_t* p_in, const uint32_t* q_in, int p_wo
     sk->hensel_ok = hbn::bitlen(p) == 32 * pl && hbn::bitlen(q) == 32 * pl &&
                     (pl == 16 || pl == 32 || pl == 48 || pl == 64);
     if (sk->hensel_ok) {
-      std::vector<uint32_t> hs_p = hensel_schedule(sp), hs_q = hensel_schedule(sq);
+      // the two-digit kernel takes its table size from the schedule: its window
+      // may differ from the generic kernels' (IPCLB200_HENSEL_WINDOW, 4..6)
+      // and is chosen per key: the width with the fewest half-width products
+      // (a squaring is 4, a multiply 5, 2^(w-1) - 1 multiplies build the table):
+      // 5 for 512-bit exponents, 6 from 1024 bits on (measured at a 2048-bit key:
+      // 80.4 -> 79.6 ms per 65536, profiles/r02_window_probe.jsonl)
+      auto cost = [](const std::vector<uint32_t>& hs) {
+        long c = 5L * ((long)hs[0] - 1);
+        for (size_t i = 2; i < hs.size(); i++)
+          c += 4L * (long)(hs[i] >> 8) + ((hs[i] & 0xffu) != 0xffu ? 5L : 0L);
+        return c;
+      };
+      int hw = 0;
+      if (const char* e = getenv("IPCLB200_HENSEL_WINDOW")) hw = atoi(e);
+      if (hw < kHenselMinWindow || hw > kHenselMaxWindow) {
+        long best = -1;
+        for (int w = kHenselMinWindow; w <= kHenselMaxWindow; w++) {
+          const long c = cost(hensel_schedule(build_schedule(pm1, w))) +
+                         cost(hensel_schedule(build_schedule(qm1, w)));
+          if (best < 0 || c < best) {
+            best = c;
+            hw = w;
+          }
+        }
+      }
+      sk->hensel_entries = std::max(16, 1 << (hw - 1));  // the constant schedule needs 16
+      std::vector<uint32_t> hs_p = hensel_schedule(build_schedule(pm1, hw)),
+                            hs_q = hensel_schedule(build_schedule(qm1, hw));
       std::vector<uint32_t> hf_p = hensel_schedule_fixed(pm1), hf_q = hensel_schedule_fixed(qm1);
       sk->h_hensel.assign(20 * (size_t)pl + hs_p.size() + hs_q.size() + hf_p.size() +
                               hf_q.size(), 0u);

@@ -61,6 +61,8 @@ def main():
                 b.record(stream)
                 stream.synchronize()
             ms = a.elapsed_time(b) / reps
+            if "IPCLB200_HENSEL_WINDOW" in os.environ:   # read at key creation
+                env = dict(env, IPCLB200_HENSEL_WINDOW=os.environ["IPCLB200_HENSEL_WINDOW"])
             print(json.dumps({"bits": bits, "count": count, "env": env, "ms": round(ms, 3),
                               "dec_per_s": round(count / ms * 1e3), "ok": ok}), flush=True)
 
