@@ -155,6 +155,20 @@ def hensel_executed_macs(p, q):
     return total
 
 
+def comb_window(key_bits=KEY_BITS):
+    """window width of the wide fixed-base table (comb_pick_window in
+    csrc/ipcl_b200.cu): the widest <= 18 bits whose table of
+    ceil(r_bits / w) * 2^w entries of 2n words fits the key's budget (4 GB)"""
+    if "IPCLB200_COMB_WINDOW" in os.environ:
+        return int(os.environ["IPCLB200_COMB_WINDOW"])
+    budget = int(os.environ.get("IPCLB200_COMB_MAX_MB", "4096")) << 20
+    r_bits, entry = key_bits // 2, 2 * key_bits // 8
+    w = 18
+    while w > 4 and ((r_bits + w - 1) // w) * (entry << w) > budget:
+        w -= 1
+    return w
+
+
 def load_key(bits=KEY_BITS):
     with open(os.path.join(ROOT, "tests", "golden", "keys.json")) as f:
         k = {a: int(b, 16) for a, b in json.load(f)[str(bits)].items()}
@@ -766,7 +780,7 @@ def main():
                 traffic = json.load(f)
         except Exception:
             pass
-        comb_w = int(os.environ.get("IPCLB200_COMB_WINDOW", "16"))
+        comb_w = comb_window()
         comb_windows = (KEY_BITS // 2 + comb_w - 1) // comb_w
         enc_exec = ((comb_windows - 1) * 5 + 5) * NL * NL
         ach = B * MAC_DECRYPT / dec_s / 1e12
@@ -825,9 +839,12 @@ def main():
                        "batch_per_gpu": B, "key_bits": KEY_BITS,
                        "l2": "256 MB flush written between timed iterations",
                        "parallelism": "shard per GPU, no data-path collective",
-                       "fixed_base_table": "16-bit windows, 2.1 GB, built once per key in "
+                       "fixed_base_table": "%d-bit windows, %.1f GB, built once per key in "
                                            "warm-up (first step incl. build: %.0f ms)"
-                                           % table_build_ms},
+                                           % (comb_window(),
+                                              ((KEY_BITS // 2 + comb_window() - 1) //
+                                               comb_window()) * (512 << comb_window()) / 2 ** 30,
+                                              table_build_ms)},
             "encrypt_per_s": total / enc_s, "decrypt_per_s": total / dec_s,
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms, "steps": args.steps,

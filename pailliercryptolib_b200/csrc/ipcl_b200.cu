@@ -978,9 +978,27 @@ int modexp_scalar(const Limbs& base, const Limbs& e, const Limbs& mod, Limbs* ou
 // fixed-base comb table of a DJN key (K5)
 // ---------------------------------------------------------------------------
 constexpr int kStarterWindow = 8;
+constexpr int kMaxCombWindow = 18;
 
 size_t comb_table_words(int L, int bits, int w) {
   return (size_t)((bits + w - 1) / w) * ((size_t)L << w);
+}
+
+// Widest window (<= kMaxCombWindow bits) whose table fits the key's budget.  B200
+// has 180 GB of HBM and the kernel needs one 4L-byte entry per window and
+// element, so the table can be large.  1024-bit r at a 2048-bit key and the
+// default 4 GB budget: w = 17 -> 61 windows x 131072 entries x 512 B = 3.9 GB and
+// 60 two-digit products per encryption (w = 16: 2.1 GB and 63).
+int comb_pick_window(const ipclb200_pubkey* pk, int bits) {
+  size_t budget_mb = pk->comb_max_mb;
+  if (const char* e = getenv("IPCLB200_COMB_MAX_MB")) budget_mb = strtoul(e, nullptr, 10);
+  int w = kMaxCombWindow;
+  while (w > 4 && comb_table_words(pk->L, bits, w) * 4 > (budget_mb << 20)) w--;
+  if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
+    int v = atoi(cw);
+    if (v >= 1 && v <= 20) w = v;
+  }
+  return w;
 }
 
 // enqueue the build of a table for `bits`-bit exponents on stream s.
@@ -989,19 +1007,8 @@ size_t comb_table_words(int L, int bits, int w) {
 int build_comb(const ipclb200_pubkey* pk, PubDev* pd, int bits, bool small, cudaStream_t s,
                CombTable* out) {
   const int L = pk->L;
-  // Widest window (<= 16 bits) whose table fits the budget.  B200 has 180 GB of
-  // HBM and the kernel needs one 4L-byte entry per window and element, so the
-  // table can be large: 1024-bit r at a 2048-bit key, w = 16 -> 64 windows x
-  // 65536 entries x 512 B = 2.1 GB and 64 multiplies per encryption.
-  size_t budget_mb = pk->comb_max_mb;
-  if (const char* e = getenv("IPCLB200_COMB_MAX_MB")) budget_mb = strtoul(e, nullptr, 10);
-  int w = 16;
-  while (w > 4 && comb_table_words(L, bits, w) * 4 > (budget_mb << 20)) w--;
-  if (small && w > kStarterWindow) w = kStarterWindow;
-  if (const char* cw = getenv("IPCLB200_COMB_WINDOW")) {
-    int v = atoi(cw);
-    if (v >= 1 && v <= 16) w = v;
-  }
+  int w = comb_pick_window(pk, bits);
+  if (small && w > kStarterWindow && !getenv("IPCLB200_COMB_WINDOW")) w = kStarterWindow;
   CombTable t;
   // the wide table of a key whose n fills its words is stored as two-digit pairs
   // (encrypt_hensel_kernel: 5/8 of the multiplies per window); it is built in
@@ -1106,6 +1113,16 @@ int build_comb(const ipclb200_pubkey* pk, PubDev* pd, int bits, bool small, cuda
   return 0;
 }
 
+// A finished wide table was converted from a full-width image of the same size
+// that went back to the stream-ordered pool (whose release threshold keeps freed
+// blocks cached): hand the unused part of the pool back to the driver, once per
+// table, so that a 3.9 GB table does not pin 7.8 GB.
+void trim_pool(Dev* dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev->id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  cudaGetLastError();
+}
+
 // The table this launch uses.  A key starts with the small table (built on the
 // caller's stream, a few ms) and, once it has encrypted `comb_upgrade_at`
 // elements, gets the wide one built on the device's side stream: encryptions
@@ -1130,6 +1147,7 @@ int comb_for_launch(const ipclb200_pubkey* pk_c, PubDev* pd, int bits, size_t co
       pd->cur = pd->next;
       pd->next = CombTable{};
       pd->next_pending = false;
+      trim_pool(pd->dev);
     } else if (q != cudaErrorNotReady) {
       return fail(IPCLB200_ERR_CUDA, std::string("comb build: ") + cudaGetErrorString(q));
     }
@@ -1159,7 +1177,8 @@ int comb_for_launch(const ipclb200_pubkey* pk_c, PubDev* pd, int bits, size_t co
       alive = pd->dev->comb_bytes;
     }
     const int tbits = std::max(bits, pk->rand_bits);
-    if (alive + comb_table_words(pk->L, tbits, 16) * 4 <= (budget_mb << 20)) {
+    if (alive + comb_table_words(pk->L, tbits, comb_pick_window(pk, tbits)) * 4 <=
+        (budget_mb << 20)) {
       // the side stream must see the constants the caller's stream may still be
       // uploading: key blocks are uploaded synchronously, nothing to wait for
       TRY(build_comb(pk, pd, tbits, false, pd->dev->side, &pd->next));
@@ -1170,6 +1189,7 @@ int comb_for_launch(const ipclb200_pubkey* pk_c, PubDev* pd, int bits, size_t co
         pd->cur = pd->next;
         pd->next = CombTable{};
         pd->next_pending = false;
+        trim_pool(pd->dev);
       }
     }
   }
