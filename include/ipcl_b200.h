@@ -130,7 +130,8 @@ void ipclb200_pubkey_destroy(ipclb200_pubkey* pk);
  * hs, the same base for every element: ipcl/pub_key.cpp:53).  A key starts with
  * a 17 MB table (8-bit windows) and, once it has encrypted `upgrade_after`
  * elements (default 8192), gets the widest table below `max_table_mb` (default
- * 4096; 16-bit windows = 2.1 GB at a 2048-bit key) built on a side stream --
+ * 4096; windows of up to 18 bits: 17 bits = 3.8 GB at a 2048-bit key, 16 bits =
+ * 2.1 GB with max_table_mb 2048..3903, 18 bits = 7.7 GB) built on a side stream --
  * encryptions keep using the small table until the wide one is ready.  Wide
  * tables of all keys on a device stay below IPCLB200_COMB_DEVICE_MB (64 GB).
  * A negative argument keeps the current value. */

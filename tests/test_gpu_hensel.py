@@ -143,7 +143,7 @@ def test_full_batch_65536_bit_exact_vs_oracle(capi, oracle, keys):
     """BASELINE.json configs[1] at full size, every element compared bit for bit
     with the oracle (AVX512-IFMA mb8 restatement, itself pinned to the ISO KAT
     and to the scalar oracle in tests/test_oracle.py): 65536 ciphertexts from
-    the 16-bit comb table the bench times, 65536 plaintexts from the two-digit
+    the wide comb table the bench times, 65536 plaintexts from the two-digit
     decrypt."""
     if not oracle.have_ifma():
         pytest.skip("host without AVX512-IFMA: the scalar oracle needs minutes for 65536")
@@ -158,7 +158,7 @@ def test_full_batch_65536_bit_exact_vs_oracle(capi, oracle, keys):
     pk = capi.PubKey(nl, hsl, 1024)
     sk = capi.PrivKey(to_limbs(p, 32), to_limbs(q, 32))
     ct = pk.encrypt(pt, r)
-    ct2 = pk.encrypt(pt, r)  # second call: the upgraded (16-bit window) table
+    ct2 = pk.encrypt(pt, r)  # second call: the upgraded (wide window) table
     want_ct = oracle.encrypt_mb8(nl, hsl, pt, r)
     assert np.array_equal(ct, want_ct)
     assert np.array_equal(ct2, want_ct)
