@@ -35,3 +35,22 @@ def test_reference_arm_other_ranks_exit_quietly():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                        timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_mirrors_of_library_choices():
+    """bench.py restates two host-side choices of the library to count the
+    multiplies a launch executes (roofline.executed_frac): the sliding-window
+    width of the two-digit decrypt (ipclb200_privkey_create) and the width of
+    the wide fixed-base table (comb_pick_window).  Pin them on the golden keys."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for bits, hw, cw in ((1024, 5, 18), (2048, 6, 17), (3072, 6, 15)):
+        p, q, _ = bench.load_key(bits)
+        assert bench.hensel_window(p, q) == hw
+        assert bench.comb_window(bits) == cw
+    p, q, _ = bench.load_key(2048)
+    nsq, nmul = bench.sliding_counts(p - 1, 6)
+    assert (nsq, nmul) == (1019, 142)
+    assert bench.hensel_executed_macs(p, q) == 10230496
+    # generic algorithm of SURVEY.md section 8(d)
+    assert bench.MAC_DECRYPT == 20854656 and bench.MAC_ENCRYPT == 1263 * (2 * 128 * 128 + 128)
